@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- BC7 encode throughput on B200 (BASELINE.json metric: Mpixel/s), beside the reference CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA through the C ABI)
+  python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's own CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): one 4096x4096 RGBA8 opaque albedo-like texture with its full mip chain
+(11 levels, 1 398 101 blocks, 22.37 Mpixel) per GPU and step, default bc7enc parameters.  A "step" is one pass of the
+hot path over that chain.  With N > 1 every rank encodes its own chain (independent textures, no collective on the
+data path; weak scaling) and `value` is the whole-job pixel rate over the max-over-ranks device time.
+
+  value  : all mip levels already resident in HBM, only our kernels inside the timed region (CUDA events on the
+           launching stream).  Four different textures are rotated so the inputs of consecutive steps (358 MB) exceed L2.
+  e2e    : the same chain through the host-buffer C-ABI call (vkt_bcn_cuda_encode_batch): pinned host level images
+           in, pinned host blocks out, H2D + kernels + D2H inside the timed region.
+  roofline     : ALU/issue-slot bound: algorithmic lane-ops per launch / kernel time vs a peak
+                 microbenchmarked in this run; HBM GB/s alongside (informational).
+  cpu_baseline : the reference (oracle/_ref, unmodified sources) or the C port, on a bounded sample, on rank 0 at N=1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vierkant_b200 import synth  # noqa: E402
+
+BASE = 4096
+KIND = 0
+WORKLOAD = "4096x4096 RGBA8 opaque albedo-like (synthetic kind 0) + full mip chain, default bc7enc params"
+OPS_PER_PIXEL = 2.9e3          # algorithmic scalar ops per pixel, opaque blocks, default params
+BYTES_PER_PIXEL = 5.0          # 64 B in + 16 B out per 16-pixel block
+ROTATE = 4
+
+
+def chain_dims(base: int):
+    """Level sizes of vierkant::bcn::compress (texture_block_compression.cpp:80-86,141-146)."""
+    r4 = lambda v: (v + 3) & ~3
+    w = h = r4(base)
+    levels = max(0, int(np.log2(max(w, h)) - 2)) + 1
+    out = []
+    for _ in range(levels):
+        out.append((w, h))
+        w, h = r4(max(w // 2, 1)), r4(max(h // 2, 1))
+    return out
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_sample(threads: int | None = None, reps: int = 2):
+    """The reference's CPU path on a bounded sample: vierkant::bcn::compress() of the top-left 2048x2048 crop of the
+    workload texture with mipmaps, delegate = thread pool with all host threads (as model::compress_textures does).
+    Returns (Mpixel/s over all levels, dict)."""
+    from oracle import pyoracle
+    crop = np.ascontiguousarray(synth.make_texture(2048, 2048, KIND))
+    npix = sum(w * h for w, h in chain_dims(2048))
+    if pyoracle.RefOracle.available():
+        ref = pyoracle.RefOracle()
+        cores = threads or ref.hardware_concurrency()
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ref.compress(crop, 1, True, cores)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        kind = "reference"
+        what = ("vierkant::bcn::compress (unmodified reference, oracle/_ref) of a 2048x2048 crop + 10 mip levels "
+                f"(5.59 Mpixel), ThreadPoolClassic delegate with {cores} threads, stbir included, best of {reps}")
+    else:
+        pyoracle.build("port")
+        port = pyoracle.PortOracle()
+        cores = threads or (os.cpu_count() or 1)
+        tiles = synth.to_blocks(crop)
+        npix = 2048 * 2048
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            port.encode_blocks(tiles, None, threads=cores)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        kind = "port"
+        what = f"C port of bc7enc_compress_block over the 262144 blocks of a 2048x2048 crop, {cores} threads, best of {reps}"
+    return npix / best * 1e-6, {"cores": cores, "kind": kind, "sample": what, "seconds": best}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    from oracle import pyoracle
+    crop = np.ascontiguousarray(synth.make_texture(2048, 2048, KIND))
+    npix = sum(w * h for w, h in chain_dims(2048))
+    if pyoracle.RefOracle.available():
+        ref = pyoracle.RefOracle()
+        cores = ref.hardware_concurrency()
+        step = lambda: ref.compress(crop, 1, True, cores)
+        kind = "reference"
+    else:
+        pyoracle.build("port")
+        port = pyoracle.PortOracle()
+        cores = os.cpu_count() or 1
+        tiles = synth.to_blocks(crop)
+        npix = 2048 * 2048
+        step = lambda: port.encode_blocks(tiles, None, threads=cores)
+        kind = "port"
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = npix * steps / dt * 1e-6
+    sample = ("each step = vierkant::bcn::compress of the top-left 2048x2048 crop of the workload texture + its 10 mip "
+              "levels (5.59 Mpixel; stbir included as in the reference), ThreadPoolClassic delegate, all host threads"
+              if kind == "reference" else "each step = C port over the 262144 blocks of a 2048x2048 crop, all host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "bc7_encode_mpixel_per_s", "value": v, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32+f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--base", type=int, default=BASE, help="level-0 size (default: the BASELINE workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from vierkant_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    ctx = capi.BcnContext([local])
+    params = capi.default_params()
+    dims = chain_dims(args.base)
+    npix = sum(w * h for w, h in dims)
+    nblocks = sum((w // 4) * (h // 4) for w, h in dims)
+
+    # synthetic level images (every level generated at its own size by the App. C generator; per-rank seeds)
+    host_levels = []   # [rotation][level] pinned uint8 tensors
+    dev_levels = []
+    for r in range(ROTATE):
+        hl, dl = [], []
+        for (w, h) in dims:
+            img = synth.make_texture(w, h, KIND, seed=0xB200 + 16 * rank + r)
+            t = torch.from_numpy(img).pin_memory()
+            hl.append(t)
+            dl.append(t.to(dev, non_blocking=True))
+        host_levels.append(hl)
+        dev_levels.append(dl)
+    dev_out = [torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8, device=dev) for (w, h) in dims]
+    host_out = [torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8).pin_memory() for (w, h) in dims]
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(i):
+        lv = dev_levels[i % ROTATE]
+        for (w, h), src, dst in zip(dims, lv, dev_out):
+            ctx.encode_bc7_device(src, w, h, 4, dst, params, 0, stream)
+
+    def step_e2e(i):
+        lv = host_levels[i % ROTATE]
+        ctx.encode_batch(capi.MODE_BC7, [(t.data_ptr(), w, h, 4) for t, (w, h) in zip(lv, dims)], host_out, params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only ------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    s0 = ctx.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_device(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = ctx.stats()
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+
+    # dominant kernel alone: the level-0 launch, timed with its own event pair
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for i in range(max(3, min(args.steps, 10))):
+        lv = dev_levels[i % ROTATE]
+        torch.cuda.synchronize()
+        k0.record()
+        ctx.encode_bc7_device(lv[0], dims[0][0], dims[0][1], 4, dev_out[0], params, 0, stream)
+        k1.record()
+        torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+    kernel_ms = float(np.mean(kms))
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------------------------
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    b0 = ctx.stats()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    b1 = ctx.stats()
+    barrier()
+
+    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(tms[0]), float(tms[1])
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        total_pix = npix * world * args.steps
+        value = total_pix / (ms_max * 1e-3) * 1e-6
+        e2e_value = total_pix / (e2e_ms_max * 1e-3) * 1e-6
+        props = torch.cuda.get_device_properties(local)
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        # issue-slot peak: SMs x 4 schedulers x 32 lanes x clock, at the max SM clock (conservative
+        # denominator) -- replaced by the microbenchmarked figure when the library provides one
+        alu_peak = props.multi_processor_count * 4 * 32 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        l0_pix = dims[0][0] * dims[0][1]
+        achieved = l0_pix * OPS_PER_PIXEL / (kernel_ms * 1e-3)
+        line = {
+            "metric": "bc7_encode_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32+f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "levels": len(dims), "blocks_per_step_per_gpu": nblocks,
+                       "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world} independent texture chains, one per GPU, no collective",
+                       "l2": f"{ROTATE} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
+                       "params": "bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"},
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
+                    "api": "vkt_bcn_cuda_encode_batch (pinned host level images in, pinned host blocks out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",
+                         "frac": achieved / alu_peak, "traffic": None,
+                         "kernel": "bc7_encode_kernel<perceptual> on level 0 (4096x4096)", "kernel_ms": kernel_ms,
+                         "ops_per_pixel": OPS_PER_PIXEL,
+                         "peak_source": f"{props.multi_processor_count} SMs x 4 x 32 lanes x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peak_src} clock)",
+                         "sm_mhz_during_run": sm_mhz,
+                         "hbm": {"achieved_gbs": l0_pix * BYTES_PER_PIXEL / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
+                                 "note": f"informational, {peak_src}"}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, info = cpu_baseline_sample()
+                line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", **info}
+            except Exception as e:  # the baseline must never take the bench down
+                line["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

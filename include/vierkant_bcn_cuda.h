@@ -1,0 +1,153 @@
+/* vierkant_bcn_cuda.h -- C ABI of libvierkant_bcn_cuda, the B200 (sm_100a) drop-in for vierkant's BCn block encoders.
+ *
+ * The reference has no FFI for this path: vierkant::bcn::compress() (src/texture_block_compression.cpp:64-154) calls
+ * the vendored bc7enc_rdo functions directly, one 4x4 block at a time:
+ *     bc7enc_compress_block_init()                          extern/bc7enc_rdo/bc7enc.h:116   (call site :34)
+ *     bc7enc_compress_block(pBlock, pPixelsRGBA, &params)   extern/bc7enc_rdo/bc7enc.h:121   (call site :132)
+ *     rgbcx::encode_bc5(pDst, pPixels, 0, 1, 4)             extern/bc7enc_rdo/rgbcx.h:266    (call site :131)
+ *     crocore::Image_<uint8_t>::resize -> stbir_resize_uint8  extern/crocore/src/Image.cpp:239-247 (call site :101)
+ * The entry points below are what a binding for that path binds instead: they take a whole level image (or a whole
+ * batch of level images) per call, because the unit a GPU wants is "all blocks of the level", not one block.
+ * INTEGRATION.md shows the C++20 wrapper that keeps vierkant::bcn::compress()'s signature on top of this ABI.
+ *
+ * Conventions
+ *   - plain C types only; the caller owns every buffer; all calls are synchronous unless a stream is passed
+ *   - return value: VKT_BCN_OK (0) or a negative VKT_BCN_ERR_* code; vkt_bcn_cuda_last_error() gives the message
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with VKT_BCN_ERR_NO_DEVICE
+ *   - output blocks are bit-identical to the reference's (same inputs, same parameters); block order is row-major,
+ *     blocks[bx + by * (width / 4)], 16 bytes each (vierkant::bcn::block_t, texture_block_compression.hpp:22-25)
+ *   - a context may be used from several host threads at once (calls are serialised per device slot)
+ */
+#ifndef VIERKANT_BCN_CUDA_H
+#define VIERKANT_BCN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKT_BCN_OK 0
+#define VKT_BCN_ERR_INVALID (-1)     /* bad argument (null pointer, size not a multiple of 4, comps not 3/4, ...) */
+#define VKT_BCN_ERR_UNSUPPORTED (-2) /* a parameter combination this encoder deliberately does not implement */
+#define VKT_BCN_ERR_CUDA (-3)        /* CUDA runtime failure, see vkt_bcn_cuda_last_error */
+#define VKT_BCN_ERR_NO_DEVICE (-4)   /* no CUDA device / driver: the library has no CPU path */
+#define VKT_BCN_ERR_OOM (-5)
+
+/* == vierkant::bcn::CompressionMode (include/vierkant/texture_block_compression.hpp:15-19) */
+#define VKT_BCN_MODE_BC5 0u
+#define VKT_BCN_MODE_BC7 1u
+
+typedef struct vkt_bcn_ctx vkt_bcn_ctx;
+
+/* Field-by-field mirror of bc7enc_compress_block_params (extern/bc7enc_rdo/bc7enc.h:14-75).  Never memcpy the C++
+ * struct across the ABI (it contains bools and padding); vkt_bc7_params_init() = bc7enc_compress_block_params_init()
+ * (bc7enc.h:95-113), which is what vierkant uses (texture_block_compression.cpp:73-74).
+ *
+ * Deliberately unsupported (VKT_BCN_ERR_UNSUPPORTED): force_selectors and quant_mode6_endpoints (only driven by
+ * bc7enc_rdo's RDO post-processor, which vierkant does not compile, src/CMakeLists.txt:11) and
+ * low_frequency_partition_weight != 1.0 (it makes the estimator's work-saving early-outs observable). */
+typedef struct vkt_bc7_params
+{
+    uint32_t mode_mask;
+    uint32_t max_partitions; /* 0..64 */
+    uint32_t weights[4];
+    uint32_t uber_level; /* 0..4 */
+    uint32_t perceptual;
+    uint32_t try_least_squares;
+    uint32_t mode17_partition_estimation_filterbank;
+    uint32_t force_alpha;
+    uint32_t force_selectors;
+    uint8_t selectors[16];
+    uint32_t quant_mode6_endpoints;
+    uint32_t bias_mode1_pbits;
+    float pbit1_weight;
+    float mode1_error_weight;
+    float mode5_error_weight;
+    float mode6_error_weight;
+    float mode7_error_weight;
+    float low_frequency_partition_weight;
+} vkt_bc7_params;
+
+void vkt_bc7_params_init(vkt_bc7_params *p);
+
+/* One level image and where its blocks go.  width and height must be multiples of 4 (vierkant::bcn::compress rounds
+ * up and resizes before encoding, texture_block_compression.cpp:80-81,101); comps is 3 or 4 (3 => alpha := 255, as
+ * get_block does, texture_block_compression.cpp:39-60); row_stride_bytes 0 means tightly packed. */
+typedef struct vkt_bcn_image
+{
+    const uint8_t *pixels;
+    uint32_t width, height, comps, row_stride_bytes;
+    void *out_blocks; /* (width / 4) * (height / 4) * 16 bytes */
+} vkt_bcn_image;
+
+/* Number of usable CUDA devices (0 if none; never fails). */
+int vkt_bcn_cuda_device_count(void);
+
+/* Create a context over `num_devices` CUDA device ordinals (devices == NULL: ordinals 0..num_devices-1; num_devices
+ * <= 0: every visible device).  Builds the encoder tables (the job of bc7enc_compress_block_init / rgbcx::init) and
+ * uploads them once per device. */
+int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devices);
+void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx);
+int vkt_bcn_cuda_num_devices(const vkt_bcn_ctx *ctx);
+
+/* Message of the last failure on this context (ctx == NULL: of the last failed create on this thread). */
+const char *vkt_bcn_cuda_last_error(const vkt_bcn_ctx *ctx);
+
+/* Replaces the per-block bc7enc_compress_block loop of one level (texture_block_compression.cpp:107-139).
+ * Host buffers in, host buffers out; block rows are split across the context's devices. params == NULL: defaults. */
+int vkt_bcn_cuda_encode_bc7(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                            uint32_t row_stride_bytes, const vkt_bc7_params *params, void *out_blocks);
+
+/* Same for the BC5 branch (rgbcx::encode_bc5(pBlock, pixels, 0, 1, 4), texture_block_compression.cpp:131). */
+int vkt_bcn_cuda_encode_bc5(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                            uint32_t row_stride_bytes, void *out_blocks);
+
+/* All levels of a mip chain, or all textures of a model, in one call (what model::compress_textures loops over,
+ * src/model/model_loading.cpp:96-118): images are distributed over the devices, copies and kernels are pipelined on
+ * per-device streams, results are gathered with async device-to-host copies.  mode is VKT_BCN_MODE_*. */
+int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_image *images, uint32_t num_images,
+                              const vkt_bc7_params *params);
+
+/* Kernel-only variants on device-resident buffers of device slot `slot` (0 <= slot < num_devices): d_pixels is
+ * RGBA8/RGB8 in HBM, d_out_blocks receives 16 B per block.  cuda_stream is a cudaStream_t (NULL = the slot's own
+ * stream, synchronised before return; otherwise the launch is asynchronous on that stream). */
+int vkt_bcn_cuda_encode_bc7_device(vkt_bcn_ctx *ctx, int slot, const void *d_pixels, uint32_t width, uint32_t height,
+                                   uint32_t comps, uint32_t row_stride_bytes, const vkt_bc7_params *params,
+                                   void *d_out_blocks, void *cuda_stream);
+int vkt_bcn_cuda_encode_bc5_device(vkt_bcn_ctx *ctx, int slot, const void *d_pixels, uint32_t width, uint32_t height,
+                                   uint32_t comps, uint32_t row_stride_bytes, void *d_out_blocks, void *cuda_stream);
+
+/* crocore::Image_<uint8_t>::resize == stbir_resize_uint8 with its defaults (extern/crocore/src/Image.cpp:239-247),
+ * bit-exact, on the GPU.  Host in / host out, tightly packed, comps 1..4. */
+int vkt_bcn_cuda_resize_u8(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                           uint8_t *out_pixels, uint32_t out_width, uint32_t out_height);
+
+/* The whole of vierkant::bcn::compress() (texture_block_compression.cpp:64-154): round the size up to a multiple of 4,
+ * resize level 0 and every further level from the previous one (on the GPU, stbir-exact), encode every level.
+ * Call vkt_bcn_cuda_compress_plan first to get the level count and per-level block counts, then pass
+ * level_blocks[l] buffers of 16 * num_blocks[l] bytes.  Only the source image crosses PCIe on the way in. */
+typedef struct vkt_bcn_plan
+{
+    uint32_t base_width, base_height, num_levels;
+    uint32_t level_width[16], level_height[16];
+    uint64_t level_num_blocks[16];
+} vkt_bcn_plan;
+int vkt_bcn_cuda_compress_plan(uint32_t width, uint32_t height, int generate_mipmaps, vkt_bcn_plan *plan);
+int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
+                          uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks);
+
+/* Counters for the measurement harness: kernels launched / bytes copied by this context since creation. */
+typedef struct vkt_bcn_stats
+{
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} vkt_bcn_stats;
+int vkt_bcn_cuda_get_stats(const vkt_bcn_ctx *ctx, vkt_bcn_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

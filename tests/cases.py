@@ -1,0 +1,87 @@
+"""Shared test inputs: edge-case tile generators and the encoder parameter matrix."""
+from __future__ import annotations
+
+import numpy as np
+
+# every knob of bc7enc_compress_block_params the C ABI accepts (SURVEY.md F10, App. E "stage-wise oracles")
+PARAM_CASES = {
+    "defaults": dict(),
+    "filterbank_off": dict(mode17_partition_estimation_filterbank=0),
+    "uber1": dict(uber_level=1),
+    "uber2": dict(uber_level=2),
+    "uber4_fb_off": dict(uber_level=4, mode17_partition_estimation_filterbank=0),
+    "partitions16": dict(max_partitions=16),
+    "partitions1": dict(max_partitions=1),
+    "partitions0": dict(max_partitions=0),
+    "no_least_squares": dict(try_least_squares=0),
+    "mode6_only": dict(mode_mask=1 << 6),
+    "modes_6_1": dict(mode_mask=(1 << 6) | (1 << 1)),
+    "modes_5_1": dict(mode_mask=(1 << 5) | (1 << 1)),
+    "modes_7_1": dict(mode_mask=(1 << 7) | (1 << 1)),
+    "force_alpha": dict(force_alpha=1),
+    "linear": dict(perceptual=0, weights=[1, 1, 1, 1]),
+    "linear_uber2": dict(perceptual=0, weights=[1, 1, 1, 1], uber_level=2),
+    "weights": dict(weights=[64, 128, 8, 77]),
+    "pbit1_weight": dict(pbit1_weight=1.5),
+    "mode_weights": dict(mode1_error_weight=0.9, mode6_error_weight=1.1, mode5_error_weight=1.2, mode7_error_weight=0.8),
+    "bias_mode1_pbits": dict(bias_mode1_pbits=1),
+}
+# accepted by the oracles only (the C ABI returns VKT_BCN_ERR_UNSUPPORTED)
+ORACLE_ONLY_CASES = {
+    "low_freq_weight": dict(low_frequency_partition_weight=0.75),
+    "quant_mode6": dict(quant_mode6_endpoints=1),
+    "force_selectors": dict(force_selectors=1, selectors=list(range(16)), mode_mask=1 << 6),
+}
+
+
+def edge_tiles(seed: int, n: int) -> np.ndarray:
+    """(12 * n, 16, 4) uint8 tiles covering the encoder's special paths: noise, solid colours (single-colour tables),
+    two-colour blocks (partitions), smooth gradients, grey ramps (degenerate endpoints), saturated / near-black values,
+    alpha-only variation (mode 5), each with and without alpha."""
+    rng = np.random.default_rng(seed)
+    t = []
+    t.append(rng.integers(0, 256, (n, 16, 4), dtype=np.uint8))
+    o = rng.integers(0, 256, (n, 16, 4), dtype=np.uint8)
+    o[..., 3] = 255
+    t.append(o)
+    s = np.repeat(rng.integers(0, 256, (n, 1, 4), dtype=np.uint8), 16, axis=1)
+    t.append(s)
+    s2 = s.copy()
+    s2[..., 3] = 255
+    t.append(s2)
+    a = rng.integers(0, 256, (n, 1, 4))
+    b = rng.integers(0, 256, (n, 1, 4))
+    m = rng.integers(0, 2, (n, 16, 1))
+    tc = np.where(m == 1, a, b).astype(np.uint8)
+    t.append(tc)
+    tc2 = tc.copy()
+    tc2[..., 3] = 255
+    t.append(tc2)
+    base = rng.integers(0, 256, (n, 1, 4))
+    dx = rng.integers(-20, 21, (n, 1, 4))
+    dy = rng.integers(-20, 21, (n, 1, 4))
+    xx = (np.arange(16) % 4).reshape(1, 16, 1)
+    yy = (np.arange(16) // 4).reshape(1, 16, 1)
+    g = np.clip(base + dx * xx + dy * yy + rng.integers(-2, 3, (n, 16, 4)), 0, 255).astype(np.uint8)
+    t.append(g)
+    g2 = g.copy()
+    g2[..., 3] = 255
+    t.append(g2)
+    gr = np.clip(rng.integers(0, 256, (n, 1, 1)) + rng.integers(-3, 4, (n, 16, 1)), 0, 255).astype(np.uint8)
+    gr = np.repeat(gr, 4, axis=2)
+    gr[..., 3] = 255
+    t.append(gr)
+    t.append(rng.integers(250, 256, (n, 16, 4), dtype=np.uint8))
+    t.append(rng.integers(0, 4, (n, 16, 4), dtype=np.uint8))
+    av = s.copy()
+    av[..., 3] = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    t.append(av)
+    return np.concatenate(t)
+
+
+def tiles_to_image(tiles: np.ndarray, blocks_x: int) -> np.ndarray:
+    """Inverse of synth.to_blocks: (n, 16, 4) tiles -> (H, W, 4) image with blocks_x tiles per row (n % blocks_x == 0)."""
+    n = tiles.shape[0]
+    assert n % blocks_x == 0
+    by = n // blocks_x
+    return np.ascontiguousarray(tiles.reshape(by, blocks_x, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(by * 4, blocks_x * 4, 4))

@@ -1,0 +1,55 @@
+// tests/host_emul/emul.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the device-side block search (vierkant_b200/csrc/bc7_core.cuh) as plain host C++ (-ffp-contract=off) so the
+// search logic can be diffed against the reference on a machine without a GPU.  Not linked into the product library;
+// the product has no CPU path.  Warp ballots degenerate to per-lane predicates here, which is the only behavioural
+// difference from the GPU build (it affects work skipping, never results).
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../vierkant_b200/csrc/bc7_core.cuh"
+#include "../../vierkant_b200/csrc/bc7_params.h"
+
+extern "C" {
+
+int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7_params *params, uint8_t *out, int threads)
+{
+    static vkt::Bc7Tables tables;
+    static bool once = (vkt::bc7_tables_build(&tables), true);
+    (void) once;
+    vkt::Bc7KernelParams kp;
+    vkt_bc7_params def;
+    if(!params)
+    {
+        vkt_bc7_params_init(&def);
+        params = &def;
+    }
+    int rc = vkt::bc7_prepare_params(params, &kp);
+    if(rc) { return rc; }
+    const bool perceptual = params->perceptual != 0;
+    auto work = [&](uint64_t b0, uint64_t b1) {
+        uint32_t texels[16], scratch[16], blk[4];
+        for(uint64_t b = b0; b < b1; ++b)
+        {
+            memcpy(texels, px + 64 * b, 64);
+            vkt::Texels<1> t{texels}, s{scratch};
+            if(perceptual) { vkt::encode_block<true, 1>(tables, kp, t, s, blk); }
+            else { vkt::encode_block<false, 1>(tables, kp, t, s, blk); }
+            memcpy(out + 16 * b, blk, 16);
+        }
+    };
+    if(threads <= 1) { work(0, num_blocks); }
+    else
+    {
+        std::vector<std::thread> pool;
+        for(int t = 0; t < threads; ++t)
+        {
+            pool.emplace_back(work, num_blocks * t / threads, num_blocks * (t + 1) / threads);
+        }
+        for(auto &t: pool) { t.join(); }
+    }
+    return 0;
+}
+}

@@ -1,0 +1,145 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Bit-exact: the work is integer/byte output."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import ORACLE_ONLY_CASES, PARAM_CASES, edge_tiles, tiles_to_image
+from oracle.pyoracle import default_params as oracle_params
+from vierkant_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_params(kw):
+    return capi.default_params(**kw)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLD, "bc7_blocks.npz"))
+
+
+@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+def test_golden_vectors(ctx, golden, case):
+    """Committed reference outputs (tests/golden/make_golden.py) for every supported parameter case."""
+    tiles = golden["tiles"]
+    n = tiles.shape[0]
+    bx = 8
+    pad = (-n) % bx
+    t = np.concatenate([tiles, np.repeat(tiles[-1:], pad, axis=0)]) if pad else tiles
+    got = ctx.encode_bc7(tiles_to_image(t, bx), gpu_params(PARAM_CASES[case]))[:n]
+    assert np.array_equal(got, golden["blocks_" + case])
+
+
+@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+@pytest.mark.parametrize("kind", [0, 1])
+def test_synthetic_texture_matches_oracle(ctx, port_oracle, case, kind):
+    img = synth.make_texture(256, 256, kind)
+    want = port_oracle.encode_blocks(synth.to_blocks(img), oracle_params(**PARAM_CASES[case]), threads=os.cpu_count() or 1)
+    got = ctx.encode_bc7(img, gpu_params(PARAM_CASES[case]))
+    mism = int((got != want).any(axis=1).sum())
+    assert mism == 0, f"{mism} / {len(want)} blocks differ"
+
+
+def test_edge_tiles_match_reference_build(ctx, ref_oracle):
+    """Against the unmodified reference itself (oracle/_ref), not just the restatement."""
+    tiles = edge_tiles(77, 128)
+    img = tiles_to_image(tiles, 32)
+    for kw in (dict(), dict(uber_level=4, mode17_partition_estimation_filterbank=0), dict(perceptual=0, weights=[1, 1, 1, 1])):
+        want = ref_oracle.encode_blocks(tiles, oracle_params(**kw), threads=os.cpu_count() or 1)
+        assert np.array_equal(ctx.encode_bc7(img, gpu_params(kw)), want)
+
+
+@pytest.mark.parametrize("w,h", [(4, 4), (8, 4), (4, 64), (260, 12), (124, 84), (36, 4)])
+def test_ragged_and_tiny_shapes(ctx, port_oracle, w, h):
+    img = synth.make_texture(w, h, 1, seed=w * 131 + h)
+    want = port_oracle.encode_blocks(synth.to_blocks(img))
+    assert np.array_equal(ctx.encode_bc7(img), want)
+
+
+def test_three_component_image_gets_opaque_alpha(ctx, port_oracle):
+    """get_block injects alpha = 255 for 3-component images (texture_block_compression.cpp:39-60)."""
+    rgba = synth.make_texture(64, 128, 1)
+    rgb = np.ascontiguousarray(rgba[..., :3])
+    opaque = rgba.copy()
+    opaque[..., 3] = 255
+    want = port_oracle.encode_blocks(synth.to_blocks(opaque))
+    assert np.array_equal(ctx.encode_bc7(rgb), want)
+
+
+def test_row_stride(ctx, port_oracle):
+    img = synth.make_texture(64, 32, 1)
+    padded = np.zeros((32, 64 * 4 + 48), dtype=np.uint8)
+    padded[:, : 64 * 4] = img.reshape(32, -1)
+    out = np.empty((8 * 16, 16), dtype=np.uint8)
+    rc = ctx.lib.vkt_bcn_cuda_encode_bc7(ctx.handle, padded.ctypes.data, 64, 32, 4, padded.shape[1], None, out.ctypes.data)
+    assert rc == 0
+    assert np.array_equal(out, port_oracle.encode_blocks(synth.to_blocks(img)))
+
+
+def test_batch_of_levels(ctx, port_oracle):
+    imgs = [synth.make_texture(s, s // 2, k, seed=s) for s, k in [(128, 0), (64, 1), (32, 1), (16, 0), (8, 1)]]
+    outs = [np.empty(((i.shape[0] // 4) * (i.shape[1] // 4), 16), dtype=np.uint8) for i in imgs]
+    ctx.encode_batch(capi.MODE_BC7, imgs, outs)
+    for i, o in zip(imgs, outs):
+        assert np.array_equal(o, port_oracle.encode_blocks(synth.to_blocks(i)))
+
+
+@pytest.mark.parametrize("name", sorted(ORACLE_ONLY_CASES))
+def test_unsupported_parameters_fail_loudly(ctx, name):
+    with pytest.raises(capi.BcnError) as e:
+        ctx.encode_bc7(synth.make_texture(8, 8, 0), gpu_params(ORACLE_ONLY_CASES[name]))
+    assert e.value.code == capi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("w,h,c", [(6, 4, 4), (4, 4, 2), (0, 4, 4)])
+def test_invalid_arguments(ctx, w, h, c):
+    buf = np.zeros(max(w * h * c, 16), dtype=np.uint8)
+    out = np.zeros(64, dtype=np.uint8)
+    rc = ctx.lib.vkt_bcn_cuda_encode_bc7(ctx.handle, buf.ctypes.data, w, h, c, 0, None, out.ctypes.data)
+    assert rc == capi.ERR_INVALID
+
+
+def test_known_answers_1024(ctx):
+    """SURVEY.md App. C inputs at the BASELINE configs[0] size: reference-derived hash and mode histogram."""
+    with open(os.path.join(GOLD, "known_answers.json")) as f:
+        known = json.load(f)
+    for entry in known["direct"]:
+        img = synth.make_texture(entry["size"], entry["size"], entry["kind"])
+        b = ctx.encode_bc7(img, gpu_params(entry["params"]))
+        assert synth.mode_histogram(b) == {int(k): v for k, v in entry["modes"].items()}
+        assert "%016x" % synth.fnv1a64_words(b) == entry["fnv1a64"], entry
+
+
+def test_device_resident_entry_point(ctx, port_oracle):
+    torch = pytest.importorskip("torch")
+    img = synth.make_texture(128, 64, 1)
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.empty(((64 // 4) * (128 // 4), 16), dtype=torch.uint8, device="cuda")
+    ctx.encode_bc7_device(d_in, 128, 64, 4, d_out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), port_oracle.encode_blocks(synth.to_blocks(img)))
+
+
+def test_full_size_properties_4096(ctx, port_oracle):
+    """BASELINE configs[1] size.  The oracle cannot encode 1 M blocks in seconds, so check size-independent properties:
+    (i) encoding is a pure per-block function: any aligned crop encodes to the same blocks as the full image;
+    (ii) a random sample of blocks matches the oracle; (iii) decoded PSNR is sane; (iv) determinism across runs."""
+    img = synth.make_texture(4096, 4096, 1)
+    full = ctx.encode_bc7(img)
+    assert np.array_equal(full, ctx.encode_bc7(img))
+    bx = 4096 // 4
+    crop = np.ascontiguousarray(img[1024:1024 + 256, 2048:2048 + 512])
+    got = ctx.encode_bc7(crop)
+    rows = (np.arange(256 // 4) + 1024 // 4)[:, None] * bx + (np.arange(512 // 4) + 2048 // 4)[None, :]
+    assert np.array_equal(got, full[rows.ravel()])
+    rng = np.random.default_rng(3)
+    idx = rng.choice(full.shape[0], 20000, replace=False)
+    tiles = synth.to_blocks(img)[idx]
+    assert np.array_equal(full[idx], port_oracle.encode_blocks(tiles, threads=os.cpu_count() or 1))
+    dec = port_oracle.unpack_blocks(full[idx]).astype(np.float64)
+    mse = ((dec - tiles.astype(np.float64)) ** 2).mean()
+    assert 10 * np.log10(255 ** 2 / mse) > 30.0

@@ -1,0 +1,1352 @@
+// bc7_core.cuh -- the per-lane BC7 block search (device code; one lane owns one 4x4 block, one warp owns a batch of 32).
+//
+// B200-native re-design of bc7enc_rdo's bc7enc_compress_block (the function vierkant::bcn::compress calls for every
+// block, /root/reference/src/texture_block_compression.cpp:132).  "bc7enc.cpp:N" = /root/reference/extern/bc7enc_rdo/bc7enc.cpp.
+//
+// Design:
+//   * lane == block.  All float work (PCA, least squares, endpoint quantisation) is inherently sequential per subset
+//     (SURVEY.md F12), so it runs once per lane with zero redundancy; the integer search loops are unrolled over the
+//     selector palette held in registers.
+//   * the partition estimator walks the candidate list warp-uniformly (every lane of the warp scores the same partition
+//     in the same iteration, membership masks live in uniform registers) and uses a warp ballot to skip candidates that
+//     no lane of the batch still needs (filterbank / checkerboard early-stop are per-lane predicates).
+//   * early-outs of the reference that only save work (estimator partial sums, subset-1 skip, mode-1 subset break)
+//     are replaced by completed sums; the argmin is identical because errors are non-negative and every comparison
+//     is strict.
+//   * texels, subset-compacted texels and the tables live in shared memory, column-per-lane (conflict-free).
+//   * bit-exactness: every float op goes through explicit round-to-nearest intrinsics (never contracted to FMA),
+//     IEEE division / sqrt, truncating conversions; operation order follows the reference expression by expression.
+//
+// The same source also compiles as plain host C++ (tests/host_emul) so that the search logic can be checked against
+// the reference on a machine without a GPU.  That build is test infrastructure; the product has no CPU path.
+#pragma once
+#include <stdint.h>
+
+#include "bc7_tables.h"
+
+#if defined(__CUDACC__)
+#define VKT_FN __host__ __device__ __forceinline__
+#define VKT_FN_NOINLINE __host__ __device__ __noinline__
+#else
+#define VKT_FN inline
+#define VKT_FN_NOINLINE
+#include <cmath>
+#endif
+
+namespace vkt
+{
+
+// ---------------------------------------------------------------------------------------------------- numerics
+#if defined(__CUDA_ARCH__)
+VKT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
+VKT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
+VKT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+VKT_FN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+VKT_FN float fsqrt(float a) { return __fsqrt_rn(a); }
+VKT_FN int f2i(float a) { return __float2int_rz(a); }// operands are always saturated first (bc7enc.cpp:871)
+VKT_FN float u64_to_f(uint64_t a) { return __ull2float_rn(a); }
+VKT_FN uint64_t f_to_u64(float a) { return __float2ull_rz(a); }
+VKT_FN int ctz32(uint32_t m) { return __ffs(m) - 1; }
+VKT_FN int popc32(uint32_t m) { return __popc(m); }
+// true if any lane of the currently converged group of the warp holds `p`
+VKT_FN bool warp_any(bool p) { return __ballot_sync(__activemask(), p) != 0u; }
+VKT_FN uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+#else
+VKT_FN float fmul(float a, float b) { return a * b; }
+VKT_FN float fadd(float a, float b) { return a + b; }
+VKT_FN float fsub(float a, float b) { return a - b; }
+VKT_FN float fdiv(float a, float b) { return a / b; }
+VKT_FN float fsqrt(float a) { return sqrtf(a); }
+VKT_FN int f2i(float a) { return (int) a; }
+VKT_FN float u64_to_f(uint64_t a) { return (float) a; }
+VKT_FN uint64_t f_to_u64(float a) { return (uint64_t) a; }
+VKT_FN int ctz32(uint32_t m) { return __builtin_ctz(m); }
+VKT_FN int popc32(uint32_t m) { return __builtin_popcount(m); }
+VKT_FN bool warp_any(bool p) { return p; }
+VKT_FN uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c)
+{
+    return c + (a & 255) * (b & 255) + ((a >> 8) & 255) * ((b >> 8) & 255) + ((a >> 16) & 255) * ((b >> 16) & 255) +
+           (a >> 24) * (b >> 24);
+}
+#endif
+
+VKT_FN float satf(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }// bc7enc.cpp:12-13 (NaN passes through)
+VKT_FN int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+VKT_FN float sqf(float v) { return fmul(v, v); }
+VKT_FN uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+VKT_FN uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+VKT_FN int imin(int a, int b) { return a < b ? a : b; }
+VKT_FN int imax(int a, int b) { return a > b ? a : b; }
+VKT_FN int iabs(int a) { return a < 0 ? -a : a; }
+
+// the (uint64)(err * weight + .5f) round trip, bc7enc.cpp:2167,2184,2234,2239,2326,2377,2382
+VKT_FN uint64_t weigh(uint64_t err, float w) { return f_to_u64(fadd(fmul(u64_to_f(err), w), .5f)); }
+
+// byte c of a packed RGBA8 word
+VKT_FN uint32_t byte_of(uint32_t v, int c) { return (v >> (8 * c)) & 255u; }
+VKT_FN uint32_t pack4(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return r | (g << 8) | (b << 16) | (a << 24); }
+
+// BC7 interpolation weight j of an N-entry palette: {0,21,43,64}, {0,9,...,64}, {0,4,9,...,64} (bc7enc.cpp:48-50)
+VKT_FN constexpr int selw(int N, int j) { return (j * 64 + (N - 1) / 2) / (N - 1); }
+
+constexpr uint64_t kNoErr = ~0ull;
+
+// ---------------------------------------------------------------------------------------------------- parameters
+// Encoder knobs after host-side preprocessing (vkt_bc7_params -> Bc7KernelParams in bcn_cuda.cu).
+struct Bc7KernelParams
+{
+    uint32_t mode_mask;
+    uint32_t max_partitions;
+    uint32_t w[4];// final integer error weights (perceptual: {w0*4, int(w1*4*pr), int(w2*4*pb), w3*4}, bc7enc.cpp:2409-2420)
+    uint32_t uber_level;
+    uint32_t try_least_squares;
+    uint32_t filterbank;
+    uint32_t force_alpha;
+    uint32_t bias_mode1_pbits;
+    float pbit1_weight;
+    float mode1_w, mode5_w, mode6_w, mode7_w;
+};
+
+// texel column of one lane: element i lives at p[i * STRIDE] (STRIDE = threads per CTA on the GPU, 1 on the host)
+template<int STRIDE>
+struct Texels
+{
+    uint32_t *p;
+    VKT_FN uint32_t operator[](int i) const { return p[i * STRIDE]; }
+    VKT_FN void set(int i, uint32_t v) const { p[i * STRIDE] = v; }
+    VKT_FN Texels offset(int i) const { return Texels{p + i * STRIDE}; }
+};
+
+// result of one colour-cell search (color_cell_compressor_results, bc7enc.cpp:477-485)
+struct Cell
+{
+    uint64_t err;
+    uint32_t lo, hi;// quantised endpoints, packed RGBA (without p-bits)
+    uint32_t pbits; // bit 0 = pbits[0], bit 1 = pbits[1]
+    uint64_t sel;   // 4 bits per texel, texel k of the cell at bits [4k, 4k+4)
+};
+
+// static description of the four cell flavours the encoder uses
+template<int MODE>
+struct ModeTraits;
+template<>
+struct ModeTraits<1>
+{
+    static constexpr int N = 8, comp_bits = 6;
+    static constexpr bool pbits = true, shared = true;
+};
+template<>
+struct ModeTraits<5>
+{
+    static constexpr int N = 4, comp_bits = 7;
+    static constexpr bool pbits = false, shared = false;
+};
+template<>
+struct ModeTraits<6>
+{
+    static constexpr int N = 16, comp_bits = 7;
+    static constexpr bool pbits = true, shared = false;
+};
+template<>
+struct ModeTraits<7>
+{
+    static constexpr int N = 4, comp_bits = 5;
+    static constexpr bool pbits = true, shared = false;
+};
+
+// ---------------------------------------------------------------------------------------------------- colour metric
+struct Ycc
+{
+    int l, cr, cb;
+};
+// bc7enc.cpp:511-516
+VKT_FN Ycc to_ycc(int r, int g, int b)
+{
+    Ycc o;
+    o.l = r * 109 + g * 366 + b * 37;
+    o.cr = (r << 9) - o.l;
+    o.cb = (b << 9) - o.l;
+    return o;
+}
+// perceptual distance (candidate e1, source e2), bc7enc.cpp:517-519,528: arithmetic shift, uint32 wrap-around products
+VKT_FN uint32_t dist_ycc(const Ycc &e1, const Ycc &e2, const uint32_t w[4])
+{
+    const int dl = (e1.l - e2.l) >> 8, dcr = (e1.cr - e2.cr) >> 8, dcb = (e1.cb - e2.cb) >> 8;
+    return w[0] * (uint32_t) (dl * dl) + w[1] * (uint32_t) (dcr * dcr) + w[2] * (uint32_t) (dcb * dcb);
+}
+// metric between two packed colours; PERC selects bc7enc.cpp:509-520 vs 521-526; ALPHA adds bc7enc.cpp:533-534.
+// The reference widens the uint32 colour term to uint64 before adding the (uint32) alpha term.
+template<bool PERC, bool ALPHA>
+VKT_FN uint64_t dist_px(uint32_t cand, uint32_t src, const uint32_t w[4])
+{
+    const int r1 = byte_of(cand, 0), g1 = byte_of(cand, 1), b1 = byte_of(cand, 2);
+    const int r2 = byte_of(src, 0), g2 = byte_of(src, 1), b2 = byte_of(src, 2);
+    uint32_t e;
+    if(PERC) { e = dist_ycc(to_ycc(r1, g1, b1), to_ycc(r2, g2, b2), w); }
+    else
+    {
+        const int dr = r1 - r2, dg = g1 - g2, db = b1 - b2;
+        e = w[0] * (uint32_t) (dr * dr) + w[1] * (uint32_t) (dg * dg) + w[2] * (uint32_t) (db * db);
+    }
+    uint64_t t = e;
+    if(ALPHA)
+    {
+        const int da = (int) byte_of(cand, 3) - (int) byte_of(src, 3);
+        t += (uint64_t) (w[3] * (uint32_t) (da * da));
+    }
+    return t;
+}
+
+// endpoint replication to 8 bits (scale_color, bc7enc.cpp:487-503) on a packed word; n = comp_bits + has_pbits
+template<int NBITS>
+VKT_FN uint32_t expand_packed(uint32_t q)
+{
+    uint32_t out = 0;
+#pragma unroll
+    for(int c = 0; c < 4; ++c)
+    {
+        uint32_t v = byte_of(q, c) << (8 - NBITS);
+        v |= v >> NBITS;
+        out |= (v & 255u) << (8 * c);
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------- single colour
+// pack_mode1_to_one_color, bc7enc.cpp:537-585
+template<bool PERC, int STRIDE>
+VKT_FN uint64_t solid_mode1(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, int n, uint32_t r, uint32_t g,
+                            uint32_t b, Cell &out)
+{
+    uint32_t best_err = 0xFFFFFFFFu, best_p = 0;
+#pragma unroll
+    for(uint32_t p = 0; p < 2; ++p)
+    {
+        const uint32_t err = (T.opt1[r][p] & 0xFFFF) + (T.opt1[g][p] & 0xFFFF) + (T.opt1[b][p] & 0xFFFF);
+        if(err < best_err) { best_err = err, best_p = p; }// the reference's break on err == 0 cannot change the argmin
+    }
+    const uint32_t er = T.opt1[r][best_p], eg = T.opt1[g][best_p], eb = T.opt1[b][best_p];
+    out.lo = pack4((er >> 16) & 255, (eg >> 16) & 255, (eb >> 16) & 255, 0);
+    out.hi = pack4(er >> 24, eg >> 24, eb >> 24, 0);
+    out.pbits = best_p;// pbits[1] = 0
+    uint64_t sel = 0;
+    for(int k = 0; k < n; ++k) { sel |= 2ull << (4 * k); }
+    out.sel = sel;
+    uint32_t c = 0;
+#pragma unroll
+    for(int i = 0; i < 3; ++i)
+    {
+        uint32_t low = ((byte_of(out.lo, i) << 1) | best_p) << 1;
+        low |= low >> 7;
+        uint32_t high = ((byte_of(out.hi, i) << 1) | best_p) << 1;
+        high |= high >> 7;
+        c |= (((low * (64 - 18) + high * 18 + 32) >> 6) & 255u) << (8 * i);
+    }
+    c |= 255u << 24;
+    uint64_t total = 0;
+    for(int k = 0; k < n; ++k) { total += dist_px<PERC, false>(c, px[k], P.w); }
+    out.err = total;
+    return total;
+}
+
+// pack_mode7_to_one_color, bc7enc.cpp:587-643
+template<bool PERC, int STRIDE>
+VKT_FN uint64_t solid_mode7(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, int n, uint32_t r, uint32_t g,
+                            uint32_t b, uint32_t a, Cell &out)
+{
+    uint32_t best_err = 0xFFFFFFFFu, best_p = 0;
+#pragma unroll
+    for(uint32_t p = 0; p < 4; ++p)
+    {
+        const uint32_t err = (T.opt7[r][p] & 0xFFFF) + (T.opt7[g][p] & 0xFFFF) + (T.opt7[b][p] & 0xFFFF) + (T.opt7[a][p] & 0xFFFF);
+        if(err < best_err) { best_err = err, best_p = p; }
+    }
+    const uint32_t hp = best_p >> 1, lp = best_p & 1;
+    const uint32_t er = T.opt7[r][best_p], eg = T.opt7[g][best_p], eb = T.opt7[b][best_p], ea = T.opt7[a][best_p];
+    out.lo = pack4((er >> 16) & 255, (eg >> 16) & 255, (eb >> 16) & 255, (ea >> 16) & 255);
+    out.hi = pack4(er >> 24, eg >> 24, eb >> 24, ea >> 24);
+    out.pbits = lp | (hp << 1);
+    uint64_t sel = 0;
+    for(int k = 0; k < n; ++k) { sel |= 1ull << (4 * k); }
+    out.sel = sel;
+    uint32_t c = 0;
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+    {
+        uint32_t low = (byte_of(out.lo, i) << 1) | lp;
+        uint32_t high = (byte_of(out.hi, i) << 1) | hp;
+        low = (low << 2) | (low >> 6);
+        high = (high << 2) | (high >> 6);
+        c |= (((low * (64 - 21) + high * 21 + 32) >> 6) & 255u) << (8 * i);
+    }
+    uint64_t total = 0;
+    for(int k = 0; k < n; ++k) { total += dist_px<PERC, true>(c, px[k], P.w); }
+    out.err = total;
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------- evaluate_solution
+// bc7enc.cpp:645-831.  lo/hi are quantised endpoints (no p-bits), pbits bit0/bit1.  Updates `best` on strict improvement.
+template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+VKT_FN void evaluate(const Bc7KernelParams &P, Texels<STRIDE> px, int n, uint32_t lo, uint32_t hi, uint32_t pbits, Cell &best)
+{
+    typedef ModeTraits<MODE> M;
+    constexpr int N = M::N;
+    uint32_t qlo = lo, qhi = hi;
+    if(M::pbits)
+    {
+        const uint32_t pl = pbits & 1u, ph = M::shared ? (pbits & 1u) : ((pbits >> 1) & 1u);
+        qlo = ((lo << 1) & 0xFEFEFEFEu) | (pl * 0x01010101u);
+        qhi = ((hi << 1) & 0xFEFEFEFEu) | (ph * 0x01010101u);
+    }
+    const uint32_t c0 = expand_packed<M::comp_bits + (M::pbits ? 1 : 0)>(qlo);
+    const uint32_t c1 = expand_packed<M::comp_bits + (M::pbits ? 1 : 0)>(qhi);
+    constexpr int NC = ALPHA ? 4 : 3;
+
+    int pal[N][NC];
+#pragma unroll
+    for(int j = 0; j < N; ++j)
+    {
+#pragma unroll
+        for(int c = 0; c < NC; ++c)
+        {
+            const int a = (int) byte_of(c0, c), b = (int) byte_of(c1, c);
+            pal[j][c] = (j == 0) ? a : (j == N - 1) ? b : ((a * (64 - selw(N, j)) + b * selw(N, j) + 32) >> 6);
+        }
+    }
+
+    uint64_t total = 0, sel = 0;
+    if(PERC)
+    {
+        Ycc ycc[N];
+#pragma unroll
+        for(int j = 0; j < N; ++j) { ycc[j] = to_ycc(pal[j][0], pal[j][1], pal[j][2]); }
+        for(int k = 0; k < n; ++k)
+        {
+            const uint32_t s = px[k];
+            const Ycc y2 = to_ycc((int) byte_of(s, 0), (int) byte_of(s, 1), (int) byte_of(s, 2));
+            const int a2 = (int) byte_of(s, 3);
+            // widened compare as in the reference (uint64 best, first strict minimum): tracked as (hi-part impossible) u64
+            uint64_t be = kNoErr;
+            uint32_t bs = 0;
+#pragma unroll
+            for(int j = 0; j < N; ++j)
+            {
+                uint64_t e = dist_ycc(ycc[j], y2, P.w);
+                if(ALPHA)
+                {
+                    const int da = pal[j][3] - a2;
+                    e += (uint64_t) (P.w[3] * (uint32_t) (da * da));
+                }
+                if(e < be) { be = e, bs = (uint32_t) j; }
+            }
+            total += be;
+            sel |= (uint64_t) bs << (4 * k);
+        }
+    }
+    else
+    {
+        // linear metric: project onto the endpoint axis, test the two nearest palette entries (bc7enc.cpp:714-777)
+        const int lr = pal[0][0], lg = pal[0][1], lb = pal[0][2];
+        const int dr = pal[N - 1][0] - lr, dg = pal[N - 1][1] - lg, db = pal[N - 1][2] - lb;
+        const int la = ALPHA ? pal[0][NC - 1] : 0, da = ALPHA ? pal[N - 1][NC - 1] - la : 0;
+        const int sq = ALPHA ? (dr * dr + dg * dg + db * db + da * da) : (dr * dr + dg * dg + db * db);
+        const float f = fdiv((float) N, fadd((float) sq, .00000125f));
+        uint32_t palp[N];
+#pragma unroll
+        for(int j = 0; j < N; ++j) { palp[j] = pack4(pal[j][0], pal[j][1], pal[j][2], ALPHA ? pal[j][NC - 1] : 0); }
+        for(int k = 0; k < n; ++k)
+        {
+            const uint32_t s = px[k];
+            const int r = byte_of(s, 0), g = byte_of(s, 1), b = byte_of(s, 2), a = byte_of(s, 3);
+            int dot = (r - lr) * dr + (g - lg) * dg + (b - lb) * db;
+            if(ALPHA) { dot += (a - la) * da; }
+            int si = f2i(fadd(fmul((float) dot, f), .5f));
+            si = clampi(si, 1, N - 1);
+            uint32_t p0 = palp[0], p1 = palp[1];
+#pragma unroll
+            for(int j = 1; j < N; ++j)
+            {
+                if(si == j) { p0 = palp[j - 1], p1 = palp[j]; }
+            }
+            const uint64_t e0 = dist_px<false, ALPHA>(p0, s, P.w), e1 = dist_px<false, ALPHA>(p1, s, P.w);
+            uint64_t be;
+            if(ALPHA)
+            {
+                be = e1;// bc7enc.cpp:737: ties keep the upper entry
+                if(e1 > e0) { be = e0, --si; }
+            }
+            else
+            {
+                be = e1;// bc7enc.cpp:766: ties keep the upper entry as well
+                if(e0 < be) { be = e0, --si; }
+            }
+            total += be;
+            sel |= (uint64_t) (uint32_t) si << (4 * k);
+        }
+    }
+
+    if(total < best.err)
+    {
+        best.err = total;
+        best.lo = lo;
+        best.hi = hi;
+        best.pbits = pbits;
+        best.sel = sel;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- find_optimal_solution
+// bc7enc.cpp:868-1099 (+ fixDegenerateEndpoints :833-866).  xl/xh are float endpoints in [0,1] (saturated here).
+template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, int n, const float xl_in[4],
+                    const float xh_in[4], Cell &best)
+{
+    typedef ModeTraits<MODE> M;
+    float xl[4], xh[4];
+#pragma unroll
+    for(int c = 0; c < 4; ++c) { xl[c] = satf(xl_in[c]), xh[c] = satf(xh_in[c]); }
+    constexpr int NCOMP = ALPHA ? 4 : 3;
+    uint32_t blo = 0, bhi = 0, bpb = 0;
+
+    if(M::pbits)
+    {
+        constexpr int iscalep = (1 << (M::comp_bits + 1)) - 1;
+        constexpr float scalep = (float) iscalep;
+        if(!M::shared)
+        {
+            // independent p-bits (modes 6, 7), bc7enc.cpp:901-973
+            float best0 = 1e+9f, best1 = 1e+9f;
+#pragma unroll
+            for(int p = 0; p < 2; ++p)
+            {
+                uint32_t qlo = 0, qhi = 0;
+                float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll
+                for(int c = 0; c < 4; ++c)
+                {
+                    int ql, qh;
+                    if(M::comp_bits == 5)
+                    {
+                        int vl = f2i(fmul(xl[c], 31.0f));
+                        vl += (xl[c] > T.mid7[vl][p]) ? 1 : 0;
+                        ql = clampi(vl * 2 + p, p, 63 - 1 + p);
+                        int vh = f2i(fmul(xh[c], 31.0f));
+                        vh += (xh[c] > T.mid7[vh][p]) ? 1 : 0;
+                        qh = clampi(vh * 2 + p, p, 63 - 1 + p);
+                    }
+                    else
+                    {
+                        ql = clampi(f2i(fadd(fdiv(fsub(fmul(xl[c], scalep), (float) p), 2.0f), .5f)) * 2 + p, p, iscalep - 1 + p);
+                        qh = clampi(f2i(fadd(fdiv(fsub(fmul(xh[c], scalep), (float) p), 2.0f), .5f)) * 2 + p, p, iscalep - 1 + p);
+                    }
+                    qlo |= (uint32_t) ql << (8 * c);
+                    qhi |= (uint32_t) qh << (8 * c);
+                }
+                const uint32_t slo = expand_packed<M::comp_bits + 1>(qlo), shi = expand_packed<M::comp_bits + 1>(qhi);
+#pragma unroll
+                for(int c = 0; c < NCOMP; ++c)
+                {
+                    e0 = fadd(e0, sqf(fsub((float) byte_of(slo, c), fmul(xl[c], 255.0f))));
+                    e1 = fadd(e1, sqf(fsub((float) byte_of(shi, c), fmul(xh[c], 255.0f))));
+                }
+                if(p == 1)
+                {
+                    e0 = fmul(e0, P.pbit1_weight);
+                    e1 = fmul(e1, P.pbit1_weight);
+                }
+                if(e0 < best0)
+                {
+                    best0 = e0;
+                    bpb = (bpb & ~1u) | (uint32_t) p;
+                    blo = (qlo >> 1) & 0x7F7F7F7Fu;
+                }
+                if(e1 < best1)
+                {
+                    best1 = e1;
+                    bpb = (bpb & ~2u) | ((uint32_t) p << 1);
+                    bhi = (qhi >> 1) & 0x7F7F7F7Fu;
+                }
+            }
+        }
+        else if(P.bias_mode1_pbits)
+        {
+            // bc7enc.cpp:977-1006
+            float x = 0.0f;
+#pragma unroll
+            for(int c = 0; c < 3; ++c)
+            {
+                const float t = x < xl[c] ? xl[c] : x;// std::max(a, b) = (a < b) ? b : a
+                x = t < xh[c] ? xh[c] : t;
+            }
+            const int p = (x > fdiv(253.0f, 255.0f)) ? 1 : 0;
+            uint32_t qlo = 0, qhi = 0;
+#pragma unroll
+            for(int c = 0; c < 4; ++c)
+            {
+                int vl = f2i(fmul(xl[c], 63.0f));
+                vl += (xl[c] > T.mid1[vl][p]) ? 1 : 0;
+                int vh = f2i(fmul(xh[c], 63.0f));
+                vh += (xh[c] > T.mid1[vh][p]) ? 1 : 0;
+                qlo |= (uint32_t) clampi(vl * 2 + p, p, 127 - 1 + p) << (8 * c);
+                qhi |= (uint32_t) clampi(vh * 2 + p, p, 127 - 1 + p) << (8 * c);
+            }
+            bpb = (uint32_t) p * 3u;
+            blo = (qlo >> 1) & 0x7F7F7F7Fu;
+            bhi = (qhi >> 1) & 0x7F7F7F7Fu;
+        }
+        else
+        {
+            // shared p-bit (mode 1), bc7enc.cpp:1009-1058
+            float beste = 1e+9f;
+#pragma unroll
+            for(int p = 0; p < 2; ++p)
+            {
+                uint32_t qlo = 0, qhi = 0;
+#pragma unroll
+                for(int c = 0; c < 4; ++c)
+                {
+                    int vl = f2i(fmul(xl[c], 63.0f));
+                    vl += (xl[c] > T.mid1[vl][p]) ? 1 : 0;
+                    int vh = f2i(fmul(xh[c], 63.0f));
+                    vh += (xh[c] > T.mid1[vh][p]) ? 1 : 0;
+                    qlo |= (uint32_t) clampi(vl * 2 + p, p, 127 - 1 + p) << (8 * c);
+                    qhi |= (uint32_t) clampi(vh * 2 + p, p, 127 - 1 + p) << (8 * c);
+                }
+                const uint32_t slo = expand_packed<7>(qlo), shi = expand_packed<7>(qhi);
+                float e = 0.0f;
+#pragma unroll
+                for(int c = 0; c < NCOMP; ++c)
+                {
+                    e = fadd(e, fadd(sqf(fsub(fdiv((float) byte_of(slo, c), 255.0f), xl[c])),
+                                     sqf(fsub(fdiv((float) byte_of(shi, c), 255.0f), xh[c]))));
+                }
+                if(p == 1) { e = fmul(e, P.pbit1_weight); }
+                if(e < beste)
+                {
+                    beste = e;
+                    bpb = (uint32_t) p * 3u;
+                    blo = (qlo >> 1) & 0x7F7F7F7Fu;
+                    bhi = (qhi >> 1) & 0x7F7F7F7Fu;
+                }
+            }
+        }
+
+        if(MODE == 1)
+        {
+            // fixDegenerateEndpoints, bc7enc.cpp:833-866, iscale = iscalep >> 1 = 63
+            constexpr uint32_t iscale = (uint32_t) (iscalep >> 1);
+#pragma unroll
+            for(int c = 0; c < 3; ++c)
+            {
+                uint32_t l = byte_of(blo, c), h = byte_of(bhi, c);
+                if(l == h && (fabsf(fsub(xl[c], xh[c])) > 0.0f))
+                {
+                    if(l > (iscale >> 1))
+                    {
+                        if(l > 0) { l--; }
+                        else if(h < iscale) { h++; }
+                    }
+                    else
+                    {
+                        if(h < iscale) { h++; }
+                        else if(l > 0) { l--; }
+                    }
+                    blo = (blo & ~(255u << (8 * c))) | (l << (8 * c));
+                    bhi = (bhi & ~(255u << (8 * c))) | (h << (8 * c));
+                }
+            }
+        }
+        const uint32_t pb_cmp_mask = 3u;
+        if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi) || ((bpb & pb_cmp_mask) != (best.pbits & pb_cmp_mask)))
+        {
+            evaluate<MODE, ALPHA, PERC, STRIDE>(P, px, n, blo, bhi, bpb, best);
+        }
+    }
+    else
+    {
+        // no p-bits (mode 5 colour, 7 bits), bc7enc.cpp:1067-1096
+#pragma unroll
+        for(int c = 0; c < 4; ++c)
+        {
+            int vl = f2i(fmul(xl[c], 127.0f));
+            vl += (xl[c] > T.mid5[vl]) ? 1 : 0;
+            int vh = f2i(fmul(xh[c], 127.0f));
+            vh += (xh[c] > T.mid5[vh]) ? 1 : 0;
+            blo |= (uint32_t) clampi(vl, 0, 127) << (8 * c);
+            bhi |= (uint32_t) clampi(vh, 0, 127) << (8 * c);
+        }
+        if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi))
+        {
+            evaluate<MODE, ALPHA, PERC, STRIDE>(P, px, n, blo, bhi, best.pbits, best);
+        }
+    }
+    return best.err;
+}
+
+// ---------------------------------------------------------------------------------------------------- least squares
+// compute_least_squares_endpoints_rgb/rgba, bc7enc.cpp:287-408, followed by the 1/255 scaling of bc7enc.cpp:1293-1294.
+// Selector k of the cell is nibble k of `sel`.  Accumulation is sequential over texels.
+template<int MODE, bool ALPHA, int STRIDE>
+VKT_FN void least_squares(const Bc7Tables &T, Texels<STRIDE> px, int n, uint64_t sel, float xl[4], float xh[4])
+{
+    constexpr int N = ModeTraits<MODE>::N;
+    constexpr int NC = ALPHA ? 4 : 3;
+    const float(*wx)[4] = (N == 4) ? T.w2x : (N == 8) ? T.w3x : T.w4x;
+    float z00 = 0.0f, z10 = 0.0f, z11 = 0.0f;
+    float q00[NC], t[NC];
+#pragma unroll
+    for(int c = 0; c < NC; ++c) { q00[c] = 0.0f, t[c] = 0.0f; }
+    for(int k = 0; k < n; ++k)
+    {
+        const uint32_t s = (uint32_t) (sel >> (4 * k)) & 15u;
+        const uint32_t v = px[k];
+        z00 = fadd(z00, wx[s][0]);
+        z10 = fadd(z10, wx[s][1]);
+        z11 = fadd(z11, wx[s][2]);
+        const float w = wx[s][3];
+#pragma unroll
+        for(int c = 0; c < NC; ++c)
+        {
+            const float pc = (float) byte_of(v, c);
+            q00[c] = fadd(q00[c], fmul(w, pc));
+            t[c] = fadd(t[c], pc);
+        }
+    }
+    const float z01 = z10;
+    float det = fsub(fmul(z00, z11), fmul(z01, z10));
+    if(det != 0.0f) { det = fdiv(1.0f, det); }
+    const float iz00 = fmul(z11, det), iz01 = fmul(-z01, det), iz10 = fmul(-z10, det), iz11 = fmul(z00, det);
+#pragma unroll
+    for(int c = 0; c < NC; ++c)
+    {
+        const float q10 = fsub(t[c], q00[c]);
+        float l = fadd(fmul(iz00, q00[c]), fmul(iz01, q10));
+        float h = fadd(fmul(iz10, q00[c]), fmul(iz11, q10));
+        if((l < 0.0f) || (h > 255.0f))
+        {
+            // rare: re-scan the channel (bc7enc.cpp:333-347)
+            uint32_t lo_v = 0xFFFFFFFFu, hi_v = 0;
+            for(int k = 0; k < n; ++k)
+            {
+                const uint32_t pc = byte_of(px[k], c);
+                lo_v = umin(lo_v, pc), hi_v = umax(hi_v, pc);
+            }
+            if(lo_v == hi_v) { l = (float) lo_v, h = (float) hi_v; }
+        }
+        xl[c] = fmul(l, fdiv(1.0f, 255.0f));
+        xh[c] = fmul(h, fdiv(1.0f, 255.0f));
+    }
+    if(!ALPHA) { xl[3] = xh[3] = fmul(255.0f, fdiv(1.0f, 255.0f)); }
+}
+
+// ---------------------------------------------------------------------------------------------------- color_cell_compression
+// bc7enc.cpp:1101-1441
+template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, int n, Cell &out)
+{
+    typedef ModeTraits<MODE> M;
+    out.err = kNoErr;
+    out.lo = out.hi = 0;
+    out.pbits = 0;
+    out.sel = 0;
+
+    const uint32_t first = px[0];
+    float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    bool same = true;
+    for(int k = 0; k < n; ++k)
+    {
+        const uint32_t v = px[k];
+        if(MODE == 7) { same = same && (v == first); }
+        else { same = same && (((v ^ first) & 0x00FFFFFFu) == 0u); }
+#pragma unroll
+        for(int c = 0; c < 4; ++c) { sum[c] = fadd(sum[c], (float) byte_of(v, c)); }
+    }
+    if(MODE == 1 && same) { return solid_mode1<PERC, STRIDE>(T, P, px, n, byte_of(first, 0), byte_of(first, 1), byte_of(first, 2), out); }
+    if(MODE == 7 && same)
+    {
+        return solid_mode7<PERC, STRIDE>(T, P, px, n, byte_of(first, 0), byte_of(first, 1), byte_of(first, 2), byte_of(first, 3), out);
+    }
+
+    // mean (bc7enc.cpp:1144-1156): sums of small integers are exact in float in any order
+    float mean_s[4], mean[4];
+    {
+        const float inv_n = fdiv(1.0f, (float) n);
+        const float inv_n255 = fdiv(1.0f, fmul((float) n, 255.0f));
+#pragma unroll
+        for(int c = 0; c < 4; ++c)
+        {
+            mean_s[c] = fmul(sum[c], inv_n);
+            mean[c] = satf(fmul(sum[c], inv_n255));
+        }
+    }
+
+    float axis[4];
+    if(ALPHA)
+    {
+        // incremental RGBA PCA, bc7enc.cpp:1160-1177
+        axis[0] = axis[1] = axis[2] = axis[3] = 0.0f;
+        for(int k = 0; k < n; ++k)
+        {
+            const uint32_t v = px[k];
+            float col[4], nrm[4];
+#pragma unroll
+            for(int c = 0; c < 4; ++c) { col[c] = fsub((float) byte_of(v, c), mean_s[c]); }
+#pragma unroll
+            for(int c = 0; c < 4; ++c) { nrm[c] = k ? axis[c] : col[c]; }
+            {
+                float s = fadd(fadd(fadd(fmul(nrm[0], nrm[0]), fmul(nrm[1], nrm[1])), fmul(nrm[2], nrm[2])), fmul(nrm[3], nrm[3]));
+                if(s != 0.0f)
+                {
+                    s = fdiv(1.0f, fsqrt(s));
+#pragma unroll
+                    for(int c = 0; c < 4; ++c) { nrm[c] = fmul(nrm[c], s); }
+                }
+            }
+#pragma unroll
+            for(int j = 0; j < 4; ++j)
+            {
+                // dot(color * color[j], n): ((a0*n0 + a1*n1) + a2*n2) + a3*n3 with a_c = color[c] * color[j]
+                const float d = fadd(fadd(fadd(fmul(fmul(col[0], col[j]), nrm[0]), fmul(fmul(col[1], col[j]), nrm[1])),
+                                          fmul(fmul(col[2], col[j]), nrm[2])),
+                                     fmul(fmul(col[3], col[j]), nrm[3]));
+                axis[j] = fadd(axis[j], d);
+            }
+        }
+        float s = fadd(fadd(fadd(fmul(axis[0], axis[0]), fmul(axis[1], axis[1])), fmul(axis[2], axis[2])), fmul(axis[3], axis[3]));
+        if(s != 0.0f)
+        {
+            s = fdiv(1.0f, fsqrt(s));
+#pragma unroll
+            for(int c = 0; c < 4; ++c) { axis[c] = fmul(axis[c], s); }
+        }
+    }
+    else
+    {
+        // covariance + 3 power iterations, bc7enc.cpp:1181-1218
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f, c5 = 0.0f;
+        for(int k = 0; k < n; ++k)
+        {
+            const uint32_t v = px[k];
+            const float r = fsub((float) byte_of(v, 0), mean_s[0]), g = fsub((float) byte_of(v, 1), mean_s[1]),
+                        b = fsub((float) byte_of(v, 2), mean_s[2]);
+            c0 = fadd(c0, fmul(r, r));
+            c1 = fadd(c1, fmul(r, g));
+            c2 = fadd(c2, fmul(r, b));
+            c3 = fadd(c3, fmul(g, g));
+            c4 = fadd(c4, fmul(g, b));
+            c5 = fadd(c5, fmul(b, b));
+        }
+        float vr = .9f, vg = 1.0f, vb = .7f;
+#pragma unroll
+        for(int it = 0; it < 3; ++it)
+        {
+            float r = fadd(fadd(fmul(vr, c0), fmul(vg, c1)), fmul(vb, c2));
+            float g = fadd(fadd(fmul(vr, c1), fmul(vg, c3)), fmul(vb, c4));
+            float b = fadd(fadd(fmul(vr, c2), fmul(vg, c4)), fmul(vb, c5));
+            float m = fabsf(r) > fabsf(g) ? fabsf(r) : fabsf(g);
+            m = m > fabsf(b) ? m : fabsf(b);
+            if(m > 1e-10f)
+            {
+                m = fdiv(1.0f, m);
+                r = fmul(r, m), g = fmul(g, m), b = fmul(b, m);
+            }
+            vr = r, vg = g, vb = b;
+        }
+        float len = fadd(fadd(fmul(vr, vr), fmul(vg, vg)), fmul(vb, vb));
+        if(len < 1e-10f) { axis[0] = axis[1] = axis[2] = axis[3] = 0.0f; }
+        else
+        {
+            len = fdiv(1.0f, fsqrt(len));
+            axis[0] = fmul(vr, len), axis[1] = fmul(vg, len), axis[2] = fmul(vb, len), axis[3] = 0.0f;
+        }
+    }
+
+    // fallback axis, bc7enc.cpp:1223-1230
+    if(fadd(fadd(fadd(fmul(axis[0], axis[0]), fmul(axis[1], axis[1])), fmul(axis[2], axis[2])), fmul(axis[3], axis[3])) < .5f)
+    {
+        if(PERC) { axis[0] = .213f, axis[1] = .715f, axis[2] = .072f, axis[3] = ALPHA ? .715f : 0.0f; }
+        else { axis[0] = 1.0f, axis[1] = 1.0f, axis[2] = 1.0f, axis[3] = ALPHA ? 1.0f : 0.0f; }
+        float s = fadd(fadd(fadd(fmul(axis[0], axis[0]), fmul(axis[1], axis[1])), fmul(axis[2], axis[2])), fmul(axis[3], axis[3]));
+        if(s != 0.0f)
+        {
+            s = fdiv(1.0f, fsqrt(s));
+#pragma unroll
+            for(int c = 0; c < 4; ++c) { axis[c] = fmul(axis[c], s); }
+        }
+    }
+
+    // projection extrema, bc7enc.cpp:1232-1246
+    float l = 1e+9f, h = -1e+9f;
+    for(int k = 0; k < n; ++k)
+    {
+        const uint32_t v = px[k];
+        float q[4];
+#pragma unroll
+        for(int c = 0; c < 4; ++c) { q[c] = fsub((float) byte_of(v, c), mean_s[c]); }
+        const float d = fadd(fadd(fadd(fmul(q[0], axis[0]), fmul(q[1], axis[1])), fmul(q[2], axis[2])), fmul(q[3], axis[3]));
+        l = (l < d) ? l : d;// minimumf / maximumf, bc7enc.cpp:17,21
+        h = (h > d) ? h : d;
+    }
+    l = fmul(l, fdiv(1.0f, 255.0f));
+    h = fmul(h, fdiv(1.0f, 255.0f));
+
+    float xl[4], xh[4];
+#pragma unroll
+    for(int c = 0; c < 4; ++c)
+    {
+        xl[c] = satf(fadd(mean[c], fmul(axis[c], l)));
+        xh[c] = satf(fadd(mean[c], fmul(axis[c], h)));
+    }
+    {
+        // bc7enc.cpp:1258: dot with (1,1,1,1) = ((x*1 + y*1) + z*1) + w*1
+        const float dl = fadd(fadd(fadd(xl[0], xl[1]), xl[2]), xl[3]);
+        const float dh = fadd(fadd(fadd(xh[0], xh[1]), xh[2]), xh[3]);
+        if(dl > dh)
+        {
+#pragma unroll
+            for(int c = 0; c < 4; ++c)
+            {
+                const float t = xl[c];
+                xl[c] = xh[c], xh[c] = t;
+            }
+        }
+    }
+
+    if(!fit<MODE, ALPHA, PERC, STRIDE>(T, P, px, n, xl, xh, out)) { return 0; }
+
+    if(P.try_least_squares)
+    {
+        least_squares<MODE, ALPHA, STRIDE>(T, px, n, out.sel, xl, xh);
+        if(!fit<MODE, ALPHA, PERC, STRIDE>(T, P, px, n, xl, xh, out)) { return 0; }
+    }
+
+    if(P.uber_level > 0)
+    {
+        // bc7enc.cpp:1300-1411
+        const uint64_t base = out.sel;
+        constexpr int max_sel_v = M::N - 1;
+        uint32_t min_sel = 16, max_sel = 0;
+        for(int k = 0; k < n; ++k)
+        {
+            const uint32_t s = (uint32_t) (base >> (4 * k)) & 15u;
+            min_sel = umin(min_sel, s);
+            max_sel = umax(max_sel, s);
+        }
+        for(int variant = 0; variant < 3; ++variant)
+        {
+            uint64_t trial = 0;
+            for(int k = 0; k < n; ++k)
+            {
+                uint32_t s = (uint32_t) (base >> (4 * k)) & 15u;
+                if(variant != 1 && (s == min_sel) && (s < (uint32_t) max_sel_v)) { s++; }
+                else if(variant != 0 && (s == max_sel) && (s > 0)) { s--; }
+                trial |= (uint64_t) s << (4 * k);
+            }
+            least_squares<MODE, ALPHA, STRIDE>(T, px, n, trial, xl, xh);
+            if(!fit<MODE, ALPHA, PERC, STRIDE>(T, P, px, n, xl, xh, out)) { return 0; }
+        }
+        const uint32_t thresh = ((uint32_t) n * 56u) >> 4;
+        if((P.uber_level >= 2) && (out.err > thresh))
+        {
+            const int Q = (P.uber_level >= 4) ? ((int) P.uber_level - 2) : 1;
+            for(int ly = -Q; ly <= 1; ++ly)
+            {
+                for(int hy = max_sel_v - 1; hy <= (max_sel_v + Q); ++hy)
+                {
+                    if((ly == 0) && (hy == max_sel_v)) { continue; }
+                    uint64_t trial = 0;
+                    const float den = fsub((float) hy, (float) ly);
+                    for(int k = 0; k < n; ++k)
+                    {
+                        const float s = (float) ((uint32_t) (base >> (4 * k)) & 15u);
+                        float v = floorf(fadd(fdiv(fmul((float) max_sel_v, fsub(s, (float) ly)), den), .5f));
+                        v = v < 0.0f ? 0.0f : (v > (float) max_sel_v ? (float) max_sel_v : v);
+                        trial |= (uint64_t) (uint32_t) f2i(v) << (4 * k);
+                    }
+                    least_squares<MODE, ALPHA, STRIDE>(T, px, n, trial, xl, xh);
+                    if(!fit<MODE, ALPHA, PERC, STRIDE>(T, P, px, n, xl, xh, out)) { return 0; }
+                }
+            }
+        }
+    }
+
+    if(MODE == 1 || MODE == 7)
+    {
+        // mean as a single colour, bc7enc.cpp:1413-1438
+        Cell avg;
+        const uint32_t r = (uint32_t) f2i(fadd(.5f, fmul(mean[0], 255.0f))), g = (uint32_t) f2i(fadd(.5f, fmul(mean[1], 255.0f))),
+                       b = (uint32_t) f2i(fadd(.5f, fmul(mean[2], 255.0f))), a = (uint32_t) f2i(fadd(.5f, fmul(mean[3], 255.0f)));
+        const uint64_t e = (MODE == 1) ? solid_mode1<PERC, STRIDE>(T, P, px, n, r, g, b, avg)
+                                       : solid_mode7<PERC, STRIDE>(T, P, px, n, r, g, b, a, avg);
+        if(e < out.err) { out = avg; }
+    }
+    return out.err;
+}
+
+// ---------------------------------------------------------------------------------------------------- partition estimate
+// One subset of color_cell_compression_est_mode1 / _mode7 (bc7enc.cpp:1443-1709), sums completed (no early-out).
+// `members` is warp-uniform: bit i set = texel i belongs to the subset.
+template<bool M7, bool PERC, int STRIDE>
+VKT_FN uint64_t estimate_subset(const Bc7KernelParams &P, Texels<STRIDE> px, uint32_t members)
+{
+    constexpr int NCH = M7 ? 4 : 3;
+    constexpr int N = M7 ? 4 : 8;
+    int lo[NCH], hi[NCH];
+#pragma unroll
+    for(int c = 0; c < NCH; ++c) { lo[c] = 255, hi[c] = 0; }
+    for(uint32_t m = members; m; m &= m - 1)
+    {
+        const uint32_t v = px[ctz32(m)];
+#pragma unroll
+        for(int c = 0; c < NCH; ++c)
+        {
+            lo[c] = imin(lo[c], (int) byte_of(v, c));
+            hi[c] = imax(hi[c], (int) byte_of(v, c));
+        }
+    }
+    int pal[N][NCH];
+#pragma unroll
+    for(int j = 0; j < N; ++j)
+    {
+#pragma unroll
+        for(int c = 0; c < NCH; ++c)
+        {
+            pal[j][c] = (j == 0) ? lo[c] : (j == N - 1) ? hi[c] : ((lo[c] * (64 - selw(N, j)) + hi[c] * selw(N, j) + 32) >> 6);
+        }
+    }
+    int ax[NCH];
+#pragma unroll
+    for(int c = 0; c < NCH; ++c) { ax[c] = hi[c] - lo[c]; }
+    int thr[N - 1];
+    {
+        int dots[N];
+#pragma unroll
+        for(int j = 0; j < N; ++j)
+        {
+            int d = 0;
+#pragma unroll
+            for(int c = 0; c < NCH; ++c) { d += pal[j][c] * ax[c]; }
+            dots[j] = d;
+        }
+#pragma unroll
+        for(int j = 0; j < N - 1; ++j) { thr[j] = (dots[j] + dots[j + 1] + 1) >> 1; }
+    }
+    Ycc ycc[N];
+    if(PERC)
+    {
+#pragma unroll
+        for(int j = 0; j < N; ++j) { ycc[j] = to_ycc(pal[j][0], pal[j][1], pal[j][2]); }
+    }
+
+    uint64_t total = 0;
+    for(uint32_t m = members; m; m &= m - 1)
+    {
+        const uint32_t v = px[ctz32(m)];
+        int ch[4];
+#pragma unroll
+        for(int c = 0; c < 4; ++c) { ch[c] = (int) byte_of(v, c); }
+        int d = 0;
+#pragma unroll
+        for(int c = 0; c < NCH; ++c) { d += ax[c] * ch[c]; }
+        // cascade "d >= thr[N-2] ? N-1 : d >= thr[N-3] ? ..." : the highest satisfied threshold wins
+        if(PERC)
+        {
+            Ycc e1 = ycc[0];
+            int a1 = M7 ? pal[0][NCH - 1] : 0;
+#pragma unroll
+            for(int j = 1; j < N; ++j)
+            {
+                if(d >= thr[j - 1])
+                {
+                    e1 = ycc[j];
+                    if(M7) { a1 = pal[j][NCH - 1]; }
+                }
+            }
+            // (ascending overwrite keeps the HIGHEST satisfied j, exactly what the reference's descending cascade picks)
+            const Ycc e2 = to_ycc(ch[0], ch[1], ch[2]);
+            const int dl = (e1.l - e2.l) >> 8, dcr = (e1.cr - e2.cr) >> 8, dcb = (e1.cb - e2.cb) >> 8;
+            // uint32 products then (int), bc7enc.cpp:1533,1670; added sign-extended to the uint64 total
+            uint32_t e = (P.w[0] * (uint32_t) dl * (uint32_t) dl) + (P.w[1] * (uint32_t) dcr * (uint32_t) dcr) +
+                         (P.w[2] * (uint32_t) dcb * (uint32_t) dcb);
+            if(M7)
+            {
+                const int dca = ch[3] - a1;
+                e += P.w[3] * (uint32_t) dca * (uint32_t) dca;
+            }
+            total += (uint64_t) (int64_t) (int32_t) e;
+        }
+        else
+        {
+            int e1[NCH];
+#pragma unroll
+            for(int c = 0; c < NCH; ++c) { e1[c] = pal[0][c]; }
+#pragma unroll
+            for(int j = 1; j < N; ++j)
+            {
+                if(d >= thr[j - 1])
+                {
+#pragma unroll
+                    for(int c = 0; c < NCH; ++c) { e1[c] = pal[j][c]; }
+                }
+            }
+            uint32_t e = 0;
+#pragma unroll
+            for(int c = 0; c < NCH; ++c)
+            {
+                const int dd = e1[c] - ch[c];
+                e += P.w[c] * (uint32_t) (dd * dd);
+            }
+            total += e;
+        }
+    }
+    return total;
+}
+
+// estimate_partition, bc7enc.cpp:1754-1838.  Warp-uniform scan; `active` lanes want a result.
+template<bool M7, bool PERC, int STRIDE>
+VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, bool active)
+{
+    const uint32_t total_partitions = umin(P.max_partitions, 64u);
+    if(total_partitions <= 1) { return 0; }
+    uint64_t best_err = kNoErr;
+    uint32_t best_partition = 0;
+    uint32_t key = 0;
+    bool running = active;
+    for(uint32_t it = 0; it < total_partitions; ++it)
+    {
+        const uint32_t part = T.order[it];
+        running = running && (best_err > 0);// loop condition of the reference
+        bool need = running;
+        if(need && P.filterbank && (it >= 14) && (it <= 34))
+        {
+            if((T.pred[part] & (1u << (key + 1))) == 0)
+            {
+                if(it == 34) { running = false; }
+                need = false;
+            }
+        }
+        if(!warp_any(need))
+        {
+            if(!warp_any(running)) { break; }
+            continue;
+        }
+        const uint32_t mask = T.part2[part];
+        uint64_t err = estimate_subset<M7, PERC, STRIDE>(P, px, (~mask) & 0xFFFFu);
+        err += estimate_subset<M7, PERC, STRIDE>(P, px, mask);
+        // bc7enc.cpp:1817-1820 with m_low_frequency_partition_weight == 1.0f (the only value the C ABI accepts) is the identity
+        if(need)
+        {
+            if(err < best_err) { best_err = err, best_partition = part; }
+            if((part == 34) && (best_partition != 34)) { running = false; }
+            if(it == 13) { key = best_partition; }
+        }
+    }
+    return best_partition;
+}
+
+// ---------------------------------------------------------------------------------------------------- bit packing
+struct Bits128
+{
+    uint64_t lo, hi;
+    uint32_t ofs;
+    VKT_FN void put(uint32_t v, uint32_t n)// LSB-first, set_block_bits bc7enc.cpp:1840-1852
+    {
+        if(ofs < 64)
+        {
+            lo |= (uint64_t) v << ofs;
+            if(ofs + n > 64) { hi |= (uint64_t) v >> (64 - ofs); }
+        }
+        else { hi |= (uint64_t) v << (ofs - 64); }
+        ofs += n;
+    }
+};
+
+struct BlockSolution
+{
+    uint32_t mode, partition;
+    uint64_t sel, asel;// 4 bits per texel, block texel order
+    uint32_t lo[2], hi[2];
+    uint32_t pbits[2];
+};
+
+// encode_bc7_block restricted to the emitted modes 1, 5, 6, 7 (bc7enc.cpp:1867-2037, layouts SURVEY.md App. B)
+VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[4])
+{
+    const uint32_t mode = s.mode;
+    const bool two = (mode == 1) || (mode == 7);
+    const uint32_t mask = two ? T.part2[s.partition] : 0u;
+    const uint32_t ibits = (mode == 6) ? 4u : (mode == 1) ? 3u : 2u;
+    const uint32_t cbits = (mode == 1) ? 6u : (mode == 7) ? 5u : 7u;
+    const uint32_t abits = (mode == 5) ? 8u : (mode == 6) ? 7u : (mode == 7) ? 5u : 0u;
+    const uint32_t top = 1u << (ibits - 1), full = (1u << ibits) - 1;
+    uint64_t sel = s.sel, asel = s.asel;
+    uint32_t lo[2] = {s.lo[0], s.lo[1]}, hi[2] = {s.hi[0], s.hi[1]}, pb[2] = {s.pbits[0], s.pbits[1]};
+    const uint32_t anchor1 = two ? T.anchor2[s.partition] : 16u;
+    // 4-bit-per-texel masks of the two subsets
+    uint64_t sub1 = 0;
+    for(int i = 0; i < 16; ++i) { sub1 |= (uint64_t) ((mask >> i) & 1u) << (4 * i); }
+    sub1 *= 15ull;
+    const uint64_t fullmask = 0x1111111111111111ull * full;
+#pragma unroll
+    for(uint32_t k = 0; k < 2; ++k)
+    {
+        if(k == 1 && !two) { break; }
+        const uint32_t a = k ? anchor1 : 0u;
+        const uint64_t members = k ? sub1 : ~sub1;
+        if((uint32_t) (sel >> (4 * a)) & top)
+        {
+            sel = (sel & ~members) | ((fullmask - sel) & members & fullmask);
+            if(mode == 5)
+            {
+                // separate alpha selectors: only RGB trades places here
+                const uint32_t l0 = lo[k], h0 = hi[k];
+                lo[k] = (h0 & 0x00FFFFFFu) | (l0 & 0xFF000000u);
+                hi[k] = (l0 & 0x00FFFFFFu) | (h0 & 0xFF000000u);
+            }
+            else
+            {
+                const uint32_t t = lo[k];
+                lo[k] = hi[k], hi[k] = t;
+            }
+            if(mode != 1) { pb[k] = ((pb[k] & 1u) << 1) | ((pb[k] >> 1) & 1u); }
+        }
+        if(mode == 5)
+        {
+            if((uint32_t) asel & 2u)
+            {
+                asel = 0x3333333333333333ull - asel;
+                const uint32_t t = lo[0];
+                lo[0] = (lo[0] & 0x00FFFFFFu) | (hi[0] & 0xFF000000u);
+                hi[0] = (hi[0] & 0x00FFFFFFu) | (t & 0xFF000000u);
+            }
+        }
+    }
+
+    Bits128 w = {0, 0, 0};
+    w.put(1u << mode, mode + 1);
+    if(mode == 5) { w.put(0, 2); }
+    if(two) { w.put(s.partition, 6); }
+    const uint32_t ncomp = (mode >= 4) ? 4u : 3u, nsub = two ? 2u : 1u;
+    for(uint32_t c = 0; c < ncomp; ++c)
+    {
+        for(uint32_t k = 0; k < nsub; ++k)
+        {
+            const uint32_t nb = (c == 3) ? abits : cbits;
+            w.put(byte_of(lo[k], (int) c), nb);
+            w.put(byte_of(hi[k], (int) c), nb);
+        }
+    }
+    if(mode != 5)
+    {
+        for(uint32_t k = 0; k < nsub; ++k)
+        {
+            w.put(pb[k] & 1u, 1);
+            if(mode != 1) { w.put((pb[k] >> 1) & 1u, 1); }
+        }
+    }
+    for(uint32_t i = 0; i < 16; ++i)
+    {
+        const uint32_t nb = (i == 0 || i == anchor1) ? ibits - 1 : ibits;
+        w.put((uint32_t) (sel >> (4 * i)) & 15u, nb);
+    }
+    if(mode == 5)
+    {
+        for(uint32_t i = 0; i < 16; ++i) { w.put((uint32_t) (asel >> (4 * i)) & 15u, i == 0 ? 1u : 2u); }
+    }
+    out[0] = (uint32_t) w.lo, out[1] = (uint32_t) (w.lo >> 32), out[2] = (uint32_t) w.hi, out[3] = (uint32_t) (w.hi >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------------- two-subset modes
+// mode 1 (bc7enc.cpp:2336-2397) / mode 7 (bc7enc.cpp:2193-2259): estimate, compact the subsets, fit both, arbitrate.
+// `sub` is a 16-texel scratch column.  Returns the weighted error, or kNoErr when not better than best_err.
+template<int MODE, bool PERC, int STRIDE>
+VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, Texels<STRIDE> sub,
+                                 uint64_t best_err, BlockSolution &sol)
+{
+    constexpr bool ALPHA = (MODE == 7);
+    const uint32_t part = estimate_partition<ALPHA, PERC, STRIDE>(T, P, px, true);
+    const uint32_t mask = T.part2[part];
+    const int n1 = popc32(mask), n0 = 16 - n1;
+    {
+        int k0 = 0, k1 = n0;
+        for(int i = 0; i < 16; ++i)
+        {
+            const uint32_t v = px[i];
+            if((mask >> i) & 1u) { sub.set(k1++, v); }
+            else { sub.set(k0++, v); }
+        }
+    }
+    Cell c0, c1;
+    const float mw = (MODE == 1) ? P.mode1_w : P.mode7_w;
+    uint64_t trial = compress_cell<MODE, ALPHA, PERC, STRIDE>(T, P, sub, n0, c0);
+    if(weigh(trial, mw) > best_err) { return kNoErr; }// bc7enc.cpp:2377/2234: not adopted either way
+    trial += compress_cell<MODE, ALPHA, PERC, STRIDE>(T, P, sub.offset(n0), n1, c1);
+    const uint64_t werr = weigh(trial, mw);
+    if(!(werr < best_err)) { return kNoErr; }
+    sol.mode = MODE;
+    sol.partition = part;
+    uint64_t sel = 0;
+    {
+        int k0 = 0, k1 = 0;
+        for(int i = 0; i < 16; ++i)
+        {
+            uint32_t s;
+            if((mask >> i) & 1u) { s = (uint32_t) (c1.sel >> (4 * k1++)) & 15u; }
+            else { s = (uint32_t) (c0.sel >> (4 * k0++)) & 15u; }
+            sel |= (uint64_t) s << (4 * i);
+        }
+    }
+    sol.sel = sel;
+    sol.asel = 0;
+    sol.lo[0] = c0.lo, sol.hi[0] = c0.hi, sol.pbits[0] = c0.pbits;
+    sol.lo[1] = c1.lo, sol.hi[1] = c1.hi, sol.pbits[1] = c1.pbits;
+    return werr;
+}
+
+// ---------------------------------------------------------------------------------------------------- mode 5 alpha
+// scalar alpha search of handle_alpha_block_mode5, bc7enc.cpp:2067-2136.  Returns the alpha error.
+template<int STRIDE>
+VKT_FN uint64_t mode5_alpha(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, uint32_t lo_a, uint32_t hi_a,
+                            uint32_t &out_lo, uint32_t &out_hi, uint64_t &out_sel)
+{
+    if(lo_a == hi_a)
+    {
+        out_lo = lo_a, out_hi = hi_a, out_sel = 0;
+        return 0;
+    }
+    uint64_t best = kNoErr;
+    const uint32_t passes = (P.uber_level >= 1) ? 3u : 2u;
+    for(uint32_t pass = 0; pass < passes; ++pass)
+    {
+        int v[4];
+        v[0] = (int) lo_a, v[3] = (int) hi_a;
+        v[1] = (v[0] * (64 - 21) + v[3] * 21 + 32) >> 6;
+        v[2] = (v[0] * (64 - 43) + v[3] * 43 + 32) >> 6;
+        uint64_t tsel = 0, terr = 0;
+        float z00 = 0.0f, z10 = 0.0f, z11 = 0.0f, q00 = 0.0f, t = 0.0f;
+        for(int i = 0; i < 16; ++i)
+        {
+            const int a = (int) byte_of(px[i], 3);
+            int s = 0;
+            int be = iabs(a - v[0]);
+            int e = iabs(a - v[1]);
+            if(e < be) { be = e, s = 1; }
+            e = iabs(a - v[2]);
+            if(e < be) { be = e, s = 2; }
+            e = iabs(a - v[3]);
+            if(e < be) { be = e, s = 3; }
+            tsel |= (uint64_t) (uint32_t) s << (4 * i);
+            terr += (uint64_t) ((uint32_t) (be * be) * P.w[3]);
+            // compute_least_squares_endpoints_a, bc7enc.cpp:410-427 (accumulated in the same texel order)
+            z00 = fadd(z00, T.w2x[s][0]);
+            z10 = fadd(z10, T.w2x[s][1]);
+            z11 = fadd(z11, T.w2x[s][2]);
+            q00 = fadd(q00, fmul(T.w2x[s][3], (float) a));
+            t = fadd(t, (float) a);
+        }
+        if(terr < best)
+        {
+            best = terr;
+            out_lo = lo_a, out_hi = hi_a, out_sel = tsel;
+        }
+        if(pass != passes - 1u)
+        {
+            const float q10 = fsub(t, q00);
+            const float z01 = z10;
+            float det = fsub(fmul(z00, z11), fmul(z01, z10));
+            if(det != 0.0f) { det = fdiv(1.0f, det); }
+            const float iz00 = fmul(z11, det), iz01 = fmul(-z01, det), iz10 = fmul(-z10, det), iz11 = fmul(z00, det);
+            const float xl = fadd(fmul(iz00, q00), fmul(iz01, q10));
+            const float xh = fadd(fmul(iz10, q00), fmul(iz11, q10));
+            // bc7enc.cpp:445-459 only acts when every alpha is equal, which cannot happen here (min_a != max_a on entry)
+            // (int)floor(x + .5f) with x86 cvttss2si semantics for out-of-range values (-> INT_MIN), then clamp
+            const float fl = floorf(fadd(xl, .5f)), fh = floorf(fadd(xh, .5f));
+            const int il = (fl >= -2147483648.0f && fl < 2147483648.0f) ? f2i(fl) : (int) 0x80000000;
+            const int ih = (fh >= -2147483648.0f && fh < 2147483648.0f) ? f2i(fh) : (int) 0x80000000;
+            uint32_t nlo = (uint32_t) clampi(il, 0, 255), nhi = (uint32_t) clampi(ih, 0, 255);
+            if(nlo > nhi)
+            {
+                const uint32_t tt = nlo;
+                nlo = nhi, nhi = tt;
+            }
+            if((nlo == lo_a) && (nhi == hi_a)) { break; }
+            lo_a = nlo, hi_a = nhi;
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------- block entry
+// bc7enc_compress_block (bc7enc.cpp:2402-2438) = handle_opaque_block (:2293-2400) | handle_alpha_block (:2139-2291).
+// px: the 16 texels of the block (packed RGBA, texel i = x + 4y), sub: scratch column.
+template<bool PERC, int STRIDE>
+VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Texels<STRIDE> px, Texels<STRIDE> sub, uint32_t out[4])
+{
+    uint32_t and_all = 0xFFFFFFFFu;
+    for(int i = 0; i < 16; ++i) { and_all &= px[i]; }
+    uint32_t min_a = 255, max_a = 0;
+    const bool alpha = P.force_alpha || ((and_all >> 24) != 255u);
+
+    BlockSolution sol;
+    sol.mode = 6, sol.partition = 0, sol.sel = 0, sol.asel = 0;
+    sol.lo[0] = sol.lo[1] = sol.hi[0] = sol.hi[1] = 0;
+    sol.pbits[0] = sol.pbits[1] = 0;
+    uint64_t best_err = kNoErr;
+
+    if(!alpha)
+    {
+        if(P.mode_mask & (1u << 6))
+        {
+            Cell c6;
+            best_err = weigh(compress_cell<6, false, PERC, STRIDE>(T, P, px, 16, c6), P.mode6_w);
+            sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
+        }
+        if((best_err > 0) && (P.max_partitions > 0) && (P.mode_mask & (1u << 1)))
+        {
+            BlockSolution s1 = sol;
+            if(two_subset_trial<1, PERC, STRIDE>(T, P, px, sub, best_err, s1) != kNoErr) { sol = s1; }
+        }
+    }
+    else
+    {
+        if(P.mode_mask & (1u << 6))
+        {
+            Cell c6;
+            best_err = weigh(compress_cell<6, true, PERC, STRIDE>(T, P, px, 16, c6), P.mode6_w);
+            sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
+        }
+        if((best_err > 0) && (P.mode_mask & (1u << 5)))
+        {
+            for(int i = 0; i < 16; ++i)
+            {
+                const uint32_t a = px[i] >> 24;
+                min_a = umin(min_a, a), max_a = umax(max_a, a);
+            }
+            Cell c5;
+            uint64_t e5 = compress_cell<5, false, PERC, STRIDE>(T, P, px, 16, c5);
+            uint32_t alo = 0, ahi = 0;
+            uint64_t asel = 0;
+            const uint64_t ea = mode5_alpha<STRIDE>(T, P, px, min_a, max_a, alo, ahi, asel);
+            e5 += ea;
+            e5 = weigh(e5, P.mode5_w);
+            if(e5 < best_err)
+            {
+                best_err = e5;
+                sol.mode = 5, sol.partition = 0;
+                sol.sel = c5.sel, sol.asel = asel;
+                sol.lo[0] = (c5.lo & 0x00FFFFFFu) | (alo << 24);
+                sol.hi[0] = (c5.hi & 0x00FFFFFFu) | (ahi << 24);
+                sol.pbits[0] = 0;
+            }
+        }
+        if((best_err > 0) && (P.mode_mask & (1u << 7)))
+        {
+            BlockSolution s7 = sol;
+            if(two_subset_trial<7, PERC, STRIDE>(T, P, px, sub, best_err, s7) != kNoErr) { sol = s7; }
+        }
+    }
+    pack_block(T, sol, out);
+}
+
+}// namespace vkt

@@ -1,0 +1,70 @@
+// bc7_params.h -- validation / preprocessing of the public vkt_bc7_params into the kernel's Bc7KernelParams.
+// Host-only, header-only; shared by the C-ABI shim (bcn_cuda.cu) and the host emulation test harness.
+#pragma once
+#include "../../include/vierkant_bcn_cuda.h"
+#include "bc7_core.cuh"
+
+inline void vkt_bc7_params_init_inline(vkt_bc7_params *p)
+{
+    // bc7enc_compress_block_params_init, /root/reference/extern/bc7enc_rdo/bc7enc.h:95-113
+    *p = vkt_bc7_params{};
+    p->mode_mask = 0xFFFFFFFFu;
+    p->max_partitions = 64;
+    p->weights[0] = 128, p->weights[1] = 64, p->weights[2] = 16, p->weights[3] = 32;
+    p->uber_level = 0;
+    p->perceptual = 1;
+    p->try_least_squares = 1;
+    p->mode17_partition_estimation_filterbank = 1;
+    p->pbit1_weight = 1.0f;
+    p->mode1_error_weight = p->mode5_error_weight = p->mode6_error_weight = p->mode7_error_weight = 1.0f;
+    p->low_frequency_partition_weight = 1.0f;
+}
+
+#ifdef VKT_BCN_DEFINE_PARAMS_INIT
+extern "C" void vkt_bc7_params_init(vkt_bc7_params *p) { vkt_bc7_params_init_inline(p); }
+#endif
+
+namespace vkt
+{
+
+// Returns VKT_BCN_OK or VKT_BCN_ERR_UNSUPPORTED.  Weight setup follows bc7enc.cpp:2409-2420 (float constant expressions
+// evaluated in float, truncating conversion) -- compile with -ffp-contract=off.
+inline int bc7_prepare_params(const vkt_bc7_params *p, Bc7KernelParams *k)
+{
+    // Knobs that only bc7enc_rdo's RDO post-processor drives and that vierkant never sets; they are rejected loudly
+    // instead of being silently ignored (see include/vierkant_bcn_cuda.h).
+    if(p->force_selectors || p->quant_mode6_endpoints) { return VKT_BCN_ERR_UNSUPPORTED; }
+    if(p->low_frequency_partition_weight != 1.0f) { return VKT_BCN_ERR_UNSUPPORTED; }
+    if(p->uber_level > 4) { return VKT_BCN_ERR_INVALID; }
+    const bool alpha_modes = (p->mode_mask & ((1u << 5) | (1u << 6) | (1u << 7))) != 0;
+    const bool opaque_modes = (p->mode_mask & ((1u << 6) | (1u << 1))) != 0;
+    if(!alpha_modes || !opaque_modes) { return VKT_BCN_ERR_INVALID; }// the reference asserts (bc7enc.cpp:2141,2295)
+    k->mode_mask = p->mode_mask;
+    k->max_partitions = p->max_partitions;
+    if(p->perceptual)
+    {
+        const float pr_weight = (.5f / (1.0f - .2126f)) * (.5f / (1.0f - .2126f));
+        const float pb_weight = (.5f / (1.0f - .0722f)) * (.5f / (1.0f - .0722f));
+        k->w[0] = (uint32_t) (int) (p->weights[0] * 4.0f);
+        k->w[1] = (uint32_t) (int) (p->weights[1] * 4.0f * pr_weight);
+        k->w[2] = (uint32_t) (int) (p->weights[2] * 4.0f * pb_weight);
+        k->w[3] = p->weights[3] * 4;
+    }
+    else
+    {
+        for(int i = 0; i < 4; ++i) { k->w[i] = p->weights[i]; }
+    }
+    k->uber_level = p->uber_level;
+    k->try_least_squares = p->try_least_squares != 0;
+    k->filterbank = p->mode17_partition_estimation_filterbank != 0;
+    k->force_alpha = p->force_alpha != 0;
+    k->bias_mode1_pbits = p->bias_mode1_pbits != 0;
+    k->pbit1_weight = p->pbit1_weight;
+    k->mode1_w = p->mode1_error_weight;
+    k->mode5_w = p->mode5_error_weight;
+    k->mode6_w = p->mode6_error_weight;
+    k->mode7_w = p->mode7_error_weight;
+    return VKT_BCN_OK;
+}
+
+}// namespace vkt

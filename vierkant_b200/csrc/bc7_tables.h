@@ -1,0 +1,39 @@
+// bc7_tables.h -- constant data of the BC7 encoder, shared by the CUDA kernels and the host-side table builder.
+//
+// One POD struct that the host fills once per context (bc7_tables_build, bc7_tables.cpp) and uploads to HBM; every
+// CTA copies it into shared memory so that lane-divergent lookups (optimal single-colour endpoints, quantiser
+// midpoints, least-squares weights, per-lane partition masks) are bank-parallel instead of serialising in the
+// constant cache.
+//
+// Reference: the tables bc7enc_compress_block_init() builds (/root/reference/extern/bc7enc_rdo/bc7enc.cpp:124-285) and
+// the static tables at bc7enc.cpp:48-105, 1714-1751, 1765-1775.
+#pragma once
+#include <stdint.h>
+
+namespace vkt
+{
+
+struct Bc7Tables
+{
+    // optimal single-colour endpoints, packed err | lo << 16 | hi << 24
+    uint32_t opt1[256][2];// [colour][pbit]              bc7enc.cpp:213-240
+    uint32_t opt7[256][4];// [colour][hi_p * 2 + lo_p]   bc7enc.cpp:242-282
+    float mid1[64][2];    // mode-1 6-bit+p quantiser midpoints   bc7enc.cpp:150-169
+    float mid7[32][2];    // mode-7 5-bit+p                       bc7enc.cpp:129-148
+    float mid5[128];      // mode-5 7-bit                         bc7enc.cpp:171-186
+    // least-squares tuples {w*w, (1-w)*w, (1-w)*(1-w), w} -- the decimal literals of bc7enc.cpp:52-57 (data!)
+    float w2x[4][4];
+    float w3x[8][4];
+    float w4x[16][4];
+    uint32_t pred[36];   // filterbank predictors bc7enc.cpp:1714-1751 (+1 pad)
+    uint16_t part2[64];  // two-subset partition masks, bit i = subset of texel i (bc7enc.cpp:60-70 packed)
+    uint8_t anchor2[64]; // bc7enc.cpp:94
+    uint8_t order[64];   // partition scan order bc7enc.cpp:1765-1775
+};
+
+static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");
+
+// Filled on the host (product code, C++): vierkant_b200/csrc/bc7_tables.cpp
+void bc7_tables_build(Bc7Tables *t);
+
+}// namespace vkt
