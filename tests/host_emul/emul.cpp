@@ -30,13 +30,13 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
     if(rc) { return rc; }
     const bool perceptual = params->perceptual != 0;
     auto work = [&](uint64_t b0, uint64_t b1) {
-        uint32_t texels[16], scratch[16], blk[4];
+        uint32_t column[64], blk[4];
         for(uint64_t b = b0; b < b1; ++b)
         {
-            memcpy(texels, px + 64 * b, 64);
-            vkt::Texels<1> t{texels}, s{scratch};
-            if(perceptual) { vkt::encode_block<true, 1>(tables, kp, t, s, blk); }
-            else { vkt::encode_block<false, 1>(tables, kp, t, s, blk); }
+            memcpy(column, px + 64 * b, 64);
+            vkt::Lane<1> lane{column};
+            if(perceptual) { vkt::encode_block<true, 1>(tables, kp, lane, blk); }
+            else { vkt::encode_block<false, 1>(tables, kp, lane, blk); }
             memcpy(out + 16 * b, blk, 16);
         }
     };

@@ -54,6 +54,14 @@ inline int bc7_prepare_params(const vkt_bc7_params *p, Bc7KernelParams *k)
     {
         for(int i = 0; i < 4; ++i) { k->w[i] = p->weights[i]; }
     }
+    {
+        // largest possible per-texel error: |dl| <= 510, |dcr| <= 803, |dcb| <= 947 (YCbCr ranges of 8-bit colours, >> 8),
+        // |da| <= 255; linear metric: 255 per channel.  Below 2^28 the kernel may fuse error and selector in one key.
+        const uint64_t b = p->perceptual ? (uint64_t) k->w[0] * 510 * 510 + (uint64_t) k->w[1] * 803 * 803 + (uint64_t) k->w[2] * 947 * 947 +
+                                                   (uint64_t) k->w[3] * 255 * 255
+                                         : ((uint64_t) k->w[0] + k->w[1] + k->w[2] + k->w[3]) * 255 * 255;
+        k->key28 = (b < (1ull << 28)) ? 1u : 0u;
+    }
     k->uber_level = p->uber_level;
     k->try_least_squares = p->try_least_squares != 0;
     k->filterbank = p->mode17_partition_estimation_filterbank != 0;

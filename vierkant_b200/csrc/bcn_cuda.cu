@@ -31,8 +31,13 @@ namespace vkt
 // fully coalesced 512-byte request of 128-bit loads.
 template<int NT>
 __device__ __forceinline__ void load_block_texels(const uint8_t *__restrict__ img, uint32_t comps, uint32_t stride, bool vec16,
-                                                  uint32_t bx, uint32_t by, Texels<NT> px)
+                                                  uint32_t bx, uint32_t by, uint32_t *col)
 {
+    struct
+    {
+        uint32_t *p;
+        __device__ __forceinline__ void set(int i, uint32_t v) const { p[i * NT] = v; }
+    } px{col};
     if(vec16)
     {
 #pragma unroll
@@ -64,8 +69,7 @@ __global__ void __launch_bounds__(NT) bc7_encode_kernel(const uint8_t *__restric
                                                          const Bc7Tables *__restrict__ g_tables, uint4 *__restrict__ out)
 {
     __shared__ __align__(16) Bc7Tables s_tables;
-    __shared__ uint32_t s_px[16 * NT];
-    __shared__ uint32_t s_sub[16 * NT];
+    __shared__ uint32_t s_lane[64 * NT];// one 64-word column per lane: texels + hoisted YCbCr (see Lane<>)
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tables);
         uint4 *dst = reinterpret_cast<uint4 *>(&s_tables);
@@ -73,11 +77,11 @@ __global__ void __launch_bounds__(NT) bc7_encode_kernel(const uint8_t *__restric
     }
     const uint32_t b = blockIdx.x * NT + threadIdx.x;
     const uint32_t bb = min(b, num_blocks - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
-    Texels<NT> px{s_px + threadIdx.x}, sub{s_sub + threadIdx.x};
-    load_block_texels<NT>(img, comps, stride, vec16 != 0, bb % blocks_x, bb / blocks_x, px);
+    Lane<NT> lane{s_lane + threadIdx.x};
+    load_block_texels<NT>(img, comps, stride, vec16 != 0, bb % blocks_x, bb / blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, NT>(s_tables, P, px, sub, blk);
+    encode_block<PERC, NT>(s_tables, P, lane, blk);
     if(b < num_blocks) { out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
