@@ -30,13 +30,22 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
     if(rc) { return rc; }
     const bool perceptual = params->perceptual != 0;
     auto work = [&](uint64_t b0, uint64_t b1) {
-        uint32_t column[64], blk[4];
+        vkt::Texel column[16];
+        uint32_t blk[4];
         for(uint64_t b = b0; b < b1; ++b)
         {
-            memcpy(column, px + 64 * b, 64);
+            for(int i = 0; i < 16; ++i) { memcpy(&column[i].px, px + 64 * b + 4 * i, 4); }
             vkt::Lane<1> lane{column};
-            if(perceptual) { vkt::encode_block<true, 1>(tables, kp, lane, blk); }
-            else { vkt::encode_block<false, 1>(tables, kp, lane, blk); }
+            if(perceptual)
+            {
+                if(kp.key28) { vkt::encode_block<true, true, 1>(tables, kp, lane, blk); }
+                else { vkt::encode_block<true, false, 1>(tables, kp, lane, blk); }
+            }
+            else
+            {
+                if(kp.key28) { vkt::encode_block<false, true, 1>(tables, kp, lane, blk); }
+                else { vkt::encode_block<false, false, 1>(tables, kp, lane, blk); }
+            }
             memcpy(out + 16 * b, blk, 16);
         }
     };

@@ -156,16 +156,25 @@ struct Bc7KernelParams
     float mode1_w, mode5_w, mode6_w, mode7_w;
 };
 
-// Per-lane column in shared memory: 64 words, element k at p[k * STRIDE] (STRIDE = threads per CTA; 1 on the host).
-//   [0,16)  packed RGBA texels (texel i = x + 4y)     [16,32) luma*  [32,48) cr*  [48,64) cb*   (* bc7enc.cpp:511-516)
+// One texel of the block with its hoisted YCbCr (bc7enc.cpp:511-516): 16 bytes, fetched with a single 128-bit shared load.
+struct alignas(16) Texel
+{
+    uint32_t px;// packed RGBA
+    int l, cr, cb;
+};
+
+// Per-lane column in shared memory: 16 texel records, texel i (= x + 4y) at p[i * STRIDE] (STRIDE = threads per CTA;
+// 1 on the host).  Consecutive lanes are 16 bytes apart, so a warp's 128-bit loads are conflict-free whatever texel
+// index each lane asks for.
 template<int STRIDE>
 struct Lane
 {
-    uint32_t *p;
-    VKT_FN uint32_t px(int i) const { return p[i * STRIDE]; }
-    VKT_FN int yl(int i) const { return (int) p[(16 + i) * STRIDE]; }
-    VKT_FN int ycr(int i) const { return (int) p[(32 + i) * STRIDE]; }
-    VKT_FN int ycb(int i) const { return (int) p[(48 + i) * STRIDE]; }
+    Texel *p;
+    VKT_FN uint32_t px(int i) const { return p[i * STRIDE].px; }
+    VKT_FN int yl(int i) const { return p[i * STRIDE].l; }
+    VKT_FN int ycr(int i) const { return p[i * STRIDE].cr; }
+    VKT_FN int ycb(int i) const { return p[i * STRIDE].cb; }
+    VKT_FN Texel at(int i) const { return p[i * STRIDE]; }
 };
 
 // A colour cell = n texels of the block, listed by the nibbles of `perm` (texel index of cell element k at bits [4k,4k+4)).
@@ -329,7 +338,7 @@ VKT_FN uint64_t solid_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<ST
 
 // ---------------------------------------------------------------------------------------------------- evaluate_solution
 // bc7enc.cpp:645-831.  lo/hi are quantised endpoints (no p-bits), pbits bit0/bit1.  Updates `best` on strict improvement.
-template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
 VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uint32_t lo, uint32_t hi, uint32_t pbits, Cell &best)
 {
     typedef ModeTraits<MODE> M;
@@ -371,7 +380,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
             pl[j] = y.l, pcr[j] = y.cr, pcb[j] = y.cb;
             pa[j] = ALPHA ? (int) byte_of(pal[j], 3) : 0;
         }
-        if(P.key28)
+        if(KEY28)
         {
             // error < 2^28 for every texel (checked on the host from the weights): key = err * 16 + j, one min per candidate.
             const uint32_t w0 = P.w[0] * 16u, w1 = P.w[1] * 16u, w2 = P.w[2] * 16u, w3 = P.w[3] * 16u;
@@ -476,7 +485,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
 
 // ---------------------------------------------------------------------------------------------------- find_optimal_solution
 // bc7enc.cpp:868-1099 (+ fixDegenerateEndpoints :833-866).  xl/xh are float endpoints in [0,1] (saturated here).
-template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
 VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, const float xl_in[4], const float xh_in[4],
                     Cell &best)
 {
@@ -637,7 +646,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi) || ((bpb & 3u) != (best.pbits & 3u)))
         {
-            evaluate<MODE, ALPHA, PERC, STRIDE>(P, L, cell, blo, bhi, bpb, best);
+            evaluate<MODE, ALPHA, PERC, KEY28, STRIDE>(P, L, cell, blo, bhi, bpb, best);
         }
     }
     else
@@ -655,7 +664,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi))
         {
-            evaluate<MODE, ALPHA, PERC, STRIDE>(P, L, cell, blo, bhi, best.pbits, best);
+            evaluate<MODE, ALPHA, PERC, KEY28, STRIDE>(P, L, cell, blo, bhi, best.pbits, best);
         }
     }
     return best.err;
@@ -720,7 +729,7 @@ VKT_FN void least_squares(const Bc7Tables &T, Lane<STRIDE> L, CellRef cell, uint
 
 // ---------------------------------------------------------------------------------------------------- color_cell_compression
 // bc7enc.cpp:1101-1441
-template<int MODE, bool ALPHA, bool PERC, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
 VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, Cell &out)
 {
     typedef ModeTraits<MODE> M;
@@ -936,7 +945,7 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             }
             least_squares<MODE, ALPHA, STRIDE>(T, L, cell, trial, xl, xh);
         }
-        if(!fit<MODE, ALPHA, PERC, STRIDE>(T, P, L, cell, xl, xh, out)) { return 0; }
+        if(!fit<MODE, ALPHA, PERC, KEY28, STRIDE>(T, P, L, cell, xl, xh, out)) { return 0; }
 
         // advance
         if(stage == 0)
@@ -985,38 +994,79 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
 
 // ---------------------------------------------------------------------------------------------------- partition estimate
 // color_cell_compression_est_mode1 / _mode7 (bc7enc.cpp:1443-1709) for BOTH subsets of one partition, sums completed.
-// `mask` is warp-uniform (bit i = subset of texel i).  All four channels are always processed: for mode 1 the block
-// is opaque (alpha == 255 everywhere), so the alpha lane has zero extent and contributes exactly nothing.
-template<bool M7, bool PERC, int STRIDE>
-VKT_FN uint64_t estimate_pair(const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t mask)
+// `part` is warp-uniform.  T.est_idx[part] lists the texels of subset 0 (ascending) then those of subset 1, so each
+// subset is a compact rolled loop over its own texels (no per-texel membership branches; the hot loop stays inside the
+// L0 instruction cache) that handles two texels per trip for instruction-level parallelism.  All four channels are
+// always processed: for mode 1 the block is opaque (alpha == 255 everywhere), so the alpha lane has zero extent and
+// contributes exactly nothing.
+//
+// One texel against the subset's palette: project, pick the entry (thresholds are non-decreasing because the palette
+// is monotone along a non-negative axis, so "highest satisfied threshold" is a balanced select tree), metric.
+template<bool M7, bool PERC, int N>
+VKT_FN uint32_t estimate_texel(const Bc7KernelParams &P, const Texel t, uint32_t axb, const uint32_t (&pal)[N], const int (&thr)[N - 1])
 {
-    constexpr int N = M7 ? 4 : 8;
-    // pass 1: bounding boxes, 16x2 SIMD lanes (r | g << 16) and (b | a << 16)
-    uint32_t lo_rg[2] = {0x00FF00FFu, 0x00FF00FFu}, lo_ba[2] = {0x00FF00FFu, 0x00FF00FFu}, hi_rg[2] = {0u, 0u}, hi_ba[2] = {0u, 0u};
-#pragma unroll
-    for(int i = 0; i < 16; ++i)
+    const int d = (int) dp4a_u8(t.px, axb, 0u);
+    uint32_t c;
+    if(N == 8)
     {
-        const uint32_t v = L.px(i);
-        const uint32_t rg = prmt(v, 0u, 0x4140u), ba = prmt(v, 0u, 0x4342u);
-        if((mask >> i) & 1u)
+        const uint32_t c01 = (d >= thr[0]) ? pal[1] : pal[0], c23 = (d >= thr[2]) ? pal[3] : pal[2];
+        const uint32_t c45 = (d >= thr[4]) ? pal[5] : pal[4], c67 = (d >= thr[6]) ? pal[7] : pal[6];
+        const uint32_t c03 = (d >= thr[1]) ? c23 : c01, c47 = (d >= thr[5]) ? c67 : c45;
+        c = (d >= thr[3]) ? c47 : c03;
+    }
+    else
+    {
+        const uint32_t c01 = (d >= thr[0]) ? pal[1] : pal[0], c23 = (d >= thr[2]) ? pal[3] : pal[2];
+        c = (d >= thr[1]) ? c23 : c01;
+    }
+    uint32_t e;
+    if(PERC)
+    {
+        const Ycc e1 = to_ycc_packed(c);
+        const int dl = (e1.l - t.l) >> 8, dcr = (e1.cr - t.cr) >> 8, dcb = (e1.cb - t.cb) >> 8;
+        // uint32 products, bc7enc.cpp:1533,1670
+        e = (P.w[0] * (uint32_t) dl * (uint32_t) dl) + (P.w[1] * (uint32_t) dcr * (uint32_t) dcr) + (P.w[2] * (uint32_t) dcb * (uint32_t) dcb);
+        if(M7)
         {
-            lo_rg[1] = vmin_u16x2(lo_rg[1], rg), hi_rg[1] = vmax_u16x2(hi_rg[1], rg);
-            lo_ba[1] = vmin_u16x2(lo_ba[1], ba), hi_ba[1] = vmax_u16x2(hi_ba[1], ba);
-        }
-        else
-        {
-            lo_rg[0] = vmin_u16x2(lo_rg[0], rg), hi_rg[0] = vmax_u16x2(hi_rg[0], rg);
-            lo_ba[0] = vmin_u16x2(lo_ba[0], ba), hi_ba[0] = vmax_u16x2(hi_ba[0], ba);
+            const int dca = (int) (t.px >> 24) - (int) (c >> 24);
+            e += P.w[3] * (uint32_t) dca * (uint32_t) dca;
         }
     }
+    else
+    {
+        e = 0;
+#pragma unroll
+        for(int ch = 0; ch < (M7 ? 4 : 3); ++ch)
+        {
+            const int dd = (int) byte_of(c, ch) - (int) byte_of(t.px, ch);
+            e += P.w[ch] * (uint32_t) (dd * dd);
+        }
+    }
+    return e;
+}
 
+template<bool M7, bool PERC, bool KEY28, int STRIDE>
+VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part)
+{
+    constexpr int N = M7 ? 4 : 8;
+    const uint8_t *order = T.est_idx[part];
+    const int n0 = (int) T.est_n0[part];
     uint64_t total = 0;
 #pragma unroll 1
     for(int s = 0; s < 2; ++s)
     {
-        const uint32_t members = s ? mask : (~mask & 0xFFFFu);
-        const uint32_t l_rg = s ? lo_rg[1] : lo_rg[0], l_ba = s ? lo_ba[1] : lo_ba[0];
-        const uint32_t h_rg = s ? hi_rg[1] : hi_rg[0], h_ba = s ? hi_ba[1] : hi_ba[0];
+        const int k0 = s ? n0 : 0, k1 = s ? 16 : n0;
+        // pass 1: bounding box, 16x2 SIMD lanes (r | g << 16) and (b | a << 16); an odd tail repeats its last texel
+        uint32_t l_rg = 0x00FF00FFu, l_ba = 0x00FF00FFu, h_rg = 0u, h_ba = 0u;
+#pragma unroll 1
+        for(int k = k0; k < k1; k += 2)
+        {
+            const uint32_t v0 = L.px(order[k]), v1 = L.px(order[(k + 1 < k1) ? k + 1 : k]);
+            const uint32_t rg0 = prmt(v0, 0u, 0x4140u), ba0 = prmt(v0, 0u, 0x4342u);
+            const uint32_t rg1 = prmt(v1, 0u, 0x4140u), ba1 = prmt(v1, 0u, 0x4342u);
+            l_rg = vmin_u16x2(l_rg, vmin_u16x2(rg0, rg1)), h_rg = vmax_u16x2(h_rg, vmax_u16x2(rg0, rg1));
+            l_ba = vmin_u16x2(l_ba, vmin_u16x2(ba0, ba1)), h_ba = vmax_u16x2(h_ba, vmax_u16x2(ba0, ba1));
+        }
         // palette: lo*(64-w) + hi*w + 32 = 64*lo + (hi-lo)*w + 32 per 16-bit lane (<= 16352: no carries between lanes)
         const uint32_t ax_rg = h_rg - l_rg, ax_ba = h_ba - l_ba;// hi >= lo per lane (subsets are never empty)
         const uint32_t axb = prmt(ax_rg, ax_ba, 0x6420u);      // (ar, ag, ab, aa) as bytes
@@ -1041,43 +1091,28 @@ VKT_FN uint64_t estimate_pair(const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t
 #pragma unroll
             for(int j = 0; j < N - 1; ++j) { thr[j] = (dots[j] + dots[j + 1] + 1) >> 1; }
         }
-
-#pragma unroll
-        for(int i = 0; i < 16; ++i)
+        // pass 2: two texels per trip; an odd tail evaluates its last texel twice and drops the copy
+        if(KEY28)
         {
-            if((members >> i) & 1u)
+            uint32_t sum = 0;// every term < 2^28 (host-checked), at most 16 terms
+#pragma unroll 1
+            for(int k = k0; k < k1; k += 2)
             {
-                const uint32_t v = L.px(i);
-                const int d = (int) dp4a_u8(v, axb, 0u);
-                // cascade "d >= thr[N-2] ? N-1 : ..." : ascending overwrite keeps the highest satisfied threshold
-                uint32_t c = pal[0];
-#pragma unroll
-                for(int j = 1; j < N; ++j) { c = (d >= thr[j - 1]) ? pal[j] : c; }
-                if(PERC)
-                {
-                    const Ycc e1 = to_ycc_packed(c);
-                    const int dl = (e1.l - L.yl(i)) >> 8, dcr = (e1.cr - L.ycr(i)) >> 8, dcb = (e1.cb - L.ycb(i)) >> 8;
-                    // uint32 products then (int), bc7enc.cpp:1533,1670; added sign-extended to the uint64 total
-                    uint32_t e = (P.w[0] * (uint32_t) dl * (uint32_t) dl) + (P.w[1] * (uint32_t) dcr * (uint32_t) dcr) +
-                                 (P.w[2] * (uint32_t) dcb * (uint32_t) dcb);
-                    if(M7)
-                    {
-                        const int dca = (int) (v >> 24) - (int) (c >> 24);
-                        e += P.w[3] * (uint32_t) dca * (uint32_t) dca;
-                    }
-                    total += (uint64_t) (int64_t) (int32_t) e;
-                }
-                else
-                {
-                    uint32_t e = 0;
-#pragma unroll
-                    for(int ch = 0; ch < (M7 ? 4 : 3); ++ch)
-                    {
-                        const int dd = (int) byte_of(c, ch) - (int) byte_of(v, ch);
-                        e += P.w[ch] * (uint32_t) (dd * dd);
-                    }
-                    total += e;
-                }
+                const bool two = (k + 1 < k1);
+                const Texel t0 = L.at(order[k]), t1 = L.at(order[two ? k + 1 : k]);
+                const uint32_t e0 = estimate_texel<M7, PERC, N>(P, t0, axb, pal, thr);
+                const uint32_t e1 = estimate_texel<M7, PERC, N>(P, t1, axb, pal, thr);
+                sum += e0 + (two ? e1 : 0u);
+            }
+            total += sum;
+        }
+        else
+        {
+#pragma unroll 1
+            for(int k = k0; k < k1; ++k)
+            {
+                const uint32_t e = estimate_texel<M7, PERC, N>(P, L.at(order[k]), axb, pal, thr);
+                total += (uint64_t) (int64_t) (int32_t) e;// `int ie; total_err += ie`, bc7enc.cpp:1533-1535
             }
         }
     }
@@ -1085,7 +1120,7 @@ VKT_FN uint64_t estimate_pair(const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t
 }
 
 // estimate_partition, bc7enc.cpp:1754-1838.  Warp-uniform scan; `active` lanes want a result.
-template<bool M7, bool PERC, int STRIDE>
+template<bool M7, bool PERC, bool KEY28, int STRIDE>
 VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool active)
 {
     const uint32_t total_partitions = umin(P.max_partitions, 64u);
@@ -1113,7 +1148,7 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
             if(!warp_any(running)) { break; }
             continue;
         }
-        const uint64_t err = estimate_pair<M7, PERC, STRIDE>(P, L, VKT_UTAB(part2)[part]);
+        const uint64_t err = estimate_pair<M7, PERC, KEY28, STRIDE>(T, P, L, part);
         // bc7enc.cpp:1817-1820 with m_low_frequency_partition_weight == 1.0f (the only value the C ABI accepts) is the identity
         if(need)
         {
@@ -1240,11 +1275,11 @@ VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[
 // ---------------------------------------------------------------------------------------------------- two-subset modes
 // mode 1 (bc7enc.cpp:2336-2397) / mode 7 (bc7enc.cpp:2193-2259): estimate, fit both subsets, arbitrate.
 // Returns the weighted error, or kNoErr when not better than best_err.
-template<int MODE, bool PERC, int STRIDE>
+template<int MODE, bool PERC, bool KEY28, int STRIDE>
 VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint64_t best_err, BlockSolution &sol)
 {
     constexpr bool ALPHA = (MODE == 7);
-    const uint32_t part = estimate_partition<ALPHA, PERC, STRIDE>(T, P, L, true);
+    const uint32_t part = estimate_partition<ALPHA, PERC, KEY28, STRIDE>(T, P, L, true);
     const uint32_t mask = T.part2[part];
     // element lists of the two subsets (ascending texel order, as the reference gathers them)
     uint64_t perm0 = 0, perm1 = 0;
@@ -1262,7 +1297,7 @@ VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, L
     {
         const CellRef cell = {s ? perm1 : perm0, s ? n1 : n0};
         Cell r;
-        trial += compress_cell<MODE, ALPHA, PERC, STRIDE>(T, P, L, cell, r);
+        trial += compress_cell<MODE, ALPHA, PERC, KEY28, STRIDE>(T, P, L, cell, r);
         if(s) { c[1] = r; }
         else { c[0] = r; }
         if(weigh(trial, mw) > best_err) { return kNoErr; }// bc7enc.cpp:2377/2234: cannot be adopted any more
@@ -1370,16 +1405,17 @@ VKT_FN void prepare_lane(Lane<STRIDE> L)
 #pragma unroll
     for(int i = 0; i < 16; ++i)
     {
-        const Ycc y = to_ycc_packed(L.p[i * STRIDE]);
-        L.p[(16 + i) * STRIDE] = (uint32_t) y.l;
-        L.p[(32 + i) * STRIDE] = (uint32_t) y.cr;
-        L.p[(48 + i) * STRIDE] = (uint32_t) y.cb;
+        Texel t;
+        t.px = L.p[i * STRIDE].px;
+        const Ycc y = to_ycc_packed(t.px);
+        t.l = y.l, t.cr = y.cr, t.cb = y.cb;
+        L.p[i * STRIDE] = t;
     }
 }
 
 // bc7enc_compress_block (bc7enc.cpp:2402-2438) = handle_opaque_block (:2293-2400) | handle_alpha_block (:2139-2291).
 // L: the lane column with texels [0,16) filled; the YCbCr rows are filled here.
-template<bool PERC, int STRIDE>
+template<bool PERC, bool KEY28, int STRIDE>
 VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
 {
     uint32_t and_all = 0xFFFFFFFFu;
@@ -1400,13 +1436,13 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if(P.mode_mask & (1u << 6))
         {
             Cell c6;
-            best_err = weigh(compress_cell<6, false, PERC, STRIDE>(T, P, L, whole, c6), P.mode6_w);
+            best_err = weigh(compress_cell<6, false, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
             sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
         }
         if((best_err > 0) && (P.max_partitions > 0) && (P.mode_mask & (1u << 1)))
         {
             BlockSolution s1 = sol;
-            if(two_subset_trial<1, PERC, STRIDE>(T, P, L, best_err, s1) != kNoErr) { sol = s1; }
+            if(two_subset_trial<1, PERC, KEY28, STRIDE>(T, P, L, best_err, s1) != kNoErr) { sol = s1; }
         }
     }
     else
@@ -1414,7 +1450,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if(P.mode_mask & (1u << 6))
         {
             Cell c6;
-            best_err = weigh(compress_cell<6, true, PERC, STRIDE>(T, P, L, whole, c6), P.mode6_w);
+            best_err = weigh(compress_cell<6, true, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
             sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
         }
         if((best_err > 0) && (P.mode_mask & (1u << 5)))
@@ -1426,7 +1462,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
                 min_a = umin(min_a, a), max_a = umax(max_a, a);
             }
             Cell c5;
-            uint64_t e5 = compress_cell<5, false, PERC, STRIDE>(T, P, L, whole, c5);
+            uint64_t e5 = compress_cell<5, false, PERC, KEY28, STRIDE>(T, P, L, whole, c5);
             uint32_t alo = 0, ahi = 0;
             uint64_t asel = 0;
             e5 += mode5_alpha<STRIDE>(T, P, L, min_a, max_a, alo, ahi, asel);
@@ -1444,7 +1480,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if((best_err > 0) && (P.mode_mask & (1u << 7)))
         {
             BlockSolution s7 = sol;
-            if(two_subset_trial<7, PERC, STRIDE>(T, P, L, best_err, s7) != kNoErr) { sol = s7; }
+            if(two_subset_trial<7, PERC, KEY28, STRIDE>(T, P, L, best_err, s7) != kNoErr) { sol = s7; }
         }
     }
     pack_block(T, sol, out);

@@ -86,6 +86,18 @@ void bc7_tables_build(Bc7Tables *t)
     std::memcpy(t->w2x, k_w2x, sizeof(k_w2x));
     std::memcpy(t->w3x, k_w3x, sizeof(k_w3x));
     std::memcpy(t->w4x, k_w4x, sizeof(k_w4x));
+    for(uint32_t p = 0; p < 64; ++p)
+    {
+        uint32_t n = 0;
+        for(uint32_t sub = 0; sub < 2; ++sub)
+        {
+            for(uint32_t i = 0; i < 16; ++i)
+            {
+                if(((k_part2[p] >> i) & 1u) == sub) { t->est_idx[p][n++] = static_cast<uint8_t>(i); }
+            }
+            if(sub == 0) { t->est_n0[p] = static_cast<uint8_t>(n); }
+        }
+    }
 
     for(uint32_t p = 0; p < 2; ++p)
     {

@@ -29,6 +29,9 @@ struct Bc7Tables
     uint16_t part2[64];  // two-subset partition masks, bit i = subset of texel i (bc7enc.cpp:60-70 packed)
     uint8_t anchor2[64]; // bc7enc.cpp:94
     uint8_t order[64];   // partition scan order bc7enc.cpp:1765-1775
+    // estimator work lists: texel indices of subset 0 (ascending) followed by those of subset 1, and |subset 0|
+    uint8_t est_idx[64][16];
+    uint8_t est_n0[64];
 };
 
 static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");

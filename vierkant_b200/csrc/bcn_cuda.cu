@@ -31,20 +31,15 @@ namespace vkt
 // fully coalesced 512-byte request of 128-bit loads.
 template<int NT>
 __device__ __forceinline__ void load_block_texels(const uint8_t *__restrict__ img, uint32_t comps, uint32_t stride, bool vec16,
-                                                  uint32_t bx, uint32_t by, uint32_t *col)
+                                                  uint32_t bx, uint32_t by, Texel *col)
 {
-    struct
-    {
-        uint32_t *p;
-        __device__ __forceinline__ void set(int i, uint32_t v) const { p[i * NT] = v; }
-    } px{col};
     if(vec16)
     {
 #pragma unroll
         for(int y = 0; y < 4; ++y)
         {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + size_t(by * 4 + y) * stride) + bx);
-            px.set(4 * y + 0, v.x), px.set(4 * y + 1, v.y), px.set(4 * y + 2, v.z), px.set(4 * y + 3, v.w);
+            col[(4 * y + 0) * NT].px = v.x, col[(4 * y + 1) * NT].px = v.y, col[(4 * y + 2) * NT].px = v.z, col[(4 * y + 3) * NT].px = v.w;
         }
     }
     else
@@ -56,20 +51,24 @@ __device__ __forceinline__ void load_block_texels(const uint8_t *__restrict__ im
             {
                 const uint8_t *t = row + x * comps;
                 const uint32_t a = (comps == 4) ? t[3] : 255u;// get_block: alpha := 255 for 3-component images
-                px.set(4 * y + x, pack4(t[0], t[1], t[2], a));
+                col[(4 * y + x) * NT].px = pack4(t[0], t[1], t[2], a);
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ BC7 kernel
-template<bool PERC, int NT>
-__global__ void __launch_bounds__(NT) bc7_encode_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks,
-                                                         uint32_t comps, uint32_t stride, int vec16, const Bc7KernelParams P,
-                                                         const Bc7Tables *__restrict__ g_tables, uint4 *__restrict__ out)
+constexpr int kBc7Threads = 256;
+constexpr int kBc7CtasPerSm = 3;// 3 x (64 KB lane columns + 8.4 KB tables) of shared memory, <= 80 registers per thread
+
+template<bool PERC, bool KEY28, int NT>
+__global__ void __launch_bounds__(NT, kBc7CtasPerSm) bc7_encode_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks,
+                                                                        uint32_t comps, uint32_t stride, int vec16, const Bc7KernelParams P,
+                                                                        const Bc7Tables *__restrict__ g_tables, uint4 *__restrict__ out)
 {
-    __shared__ __align__(16) Bc7Tables s_tables;
-    __shared__ uint32_t s_lane[64 * NT];// one 64-word column per lane: texels + hoisted YCbCr (see Lane<>)
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Bc7Tables &s_tables = *reinterpret_cast<Bc7Tables *>(s_raw);
+    Texel *s_lane = reinterpret_cast<Texel *>(s_raw + sizeof(Bc7Tables));// one 16-record column per lane (see Lane<>)
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tables);
         uint4 *dst = reinterpret_cast<uint4 *>(&s_tables);
@@ -81,11 +80,21 @@ __global__ void __launch_bounds__(NT) bc7_encode_kernel(const uint8_t *__restric
     load_block_texels<NT>(img, comps, stride, vec16 != 0, bb % blocks_x, bb / blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, NT>(s_tables, P, lane, blk);
+    encode_block<PERC, KEY28, NT>(s_tables, P, lane, blk);
     if(b < num_blocks) { out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
-constexpr int kBc7Threads = 128;
+constexpr size_t kBc7SmemBytes = sizeof(Bc7Tables) + size_t(kBc7Threads) * 16 * sizeof(Texel);
+
+// > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
+static cudaError_t bc7_kernel_attributes()
+{
+    cudaError_t e = cudaFuncSetAttribute(bc7_encode_kernel<true, true, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
+    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<true, false, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
+    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<false, true, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
+    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<false, false, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
+    return e;
+}
 
 // ------------------------------------------------------------------------------------------------ context
 struct DeviceSlot
@@ -188,15 +197,19 @@ static int launch_bc7(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_
     const uint32_t bx = w / 4, nblocks = bx * (h / 4);
     const int vec16 = (comps == 4) && ((stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_px) & 15u) == 0);
     const uint32_t grid = (nblocks + kBc7Threads - 1) / kBc7Threads;
+    auto go = [&](auto kernel) {
+        kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(static_cast<const uint8_t *>(d_px), bx, nblocks, comps, stride, vec16, kp,
+                                                           s->d_tables, static_cast<uint4 *>(d_out));
+    };
     if(params->perceptual)
     {
-        bc7_encode_kernel<true, kBc7Threads><<<grid, kBc7Threads, 0, stream>>>(static_cast<const uint8_t *>(d_px), bx, nblocks, comps, stride,
-                                                                             vec16, kp, s->d_tables, static_cast<uint4 *>(d_out));
+        if(kp.key28) { go(bc7_encode_kernel<true, true, kBc7Threads>); }
+        else { go(bc7_encode_kernel<true, false, kBc7Threads>); }
     }
     else
     {
-        bc7_encode_kernel<false, kBc7Threads><<<grid, kBc7Threads, 0, stream>>>(static_cast<const uint8_t *>(d_px), bx, nblocks, comps, stride,
-                                                                              vec16, kp, s->d_tables, static_cast<uint4 *>(d_out));
+        if(kp.key28) { go(bc7_encode_kernel<false, true, kBc7Threads>); }
+        else { go(bc7_encode_kernel<false, false, kBc7Threads>); }
     }
     VKT_CUDA(ctx, cudaGetLastError());
     count(ctx, 1, 0, 0);
@@ -295,6 +308,7 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
         if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
+        if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
         if(e != cudaSuccess)
         {
             fail(nullptr, VKT_BCN_ERR_CUDA, "device %d initialisation failed: %s", dev, cudaGetErrorString(e));
