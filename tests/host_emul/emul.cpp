@@ -36,15 +36,20 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
         {
             for(int i = 0; i < 16; ++i) { memcpy(&column[i].px, px + 64 * b + 4 * i, 4); }
             vkt::Lane<1> lane{column};
-            if(perceptual)
+            uint32_t raw[16];
+            memcpy(raw, px + 64 * b, 64);
+            const bool alpha = vkt::block_has_alpha(kp, raw);
+            const int sel = (perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            switch(sel)
             {
-                if(kp.key28) { vkt::encode_block<true, true, 1>(tables, kp, lane, blk); }
-                else { vkt::encode_block<true, false, 1>(tables, kp, lane, blk); }
-            }
-            else
-            {
-                if(kp.key28) { vkt::encode_block<false, true, 1>(tables, kp, lane, blk); }
-                else { vkt::encode_block<false, false, 1>(tables, kp, lane, blk); }
+                case 7: vkt::encode_block<true, true, true, 1>(tables, kp, lane, blk); break;
+                case 6: vkt::encode_block<true, true, false, 1>(tables, kp, lane, blk); break;
+                case 5: vkt::encode_block<true, false, true, 1>(tables, kp, lane, blk); break;
+                case 4: vkt::encode_block<true, false, false, 1>(tables, kp, lane, blk); break;
+                case 3: vkt::encode_block<false, true, true, 1>(tables, kp, lane, blk); break;
+                case 2: vkt::encode_block<false, true, false, 1>(tables, kp, lane, blk); break;
+                case 1: vkt::encode_block<false, false, true, 1>(tables, kp, lane, blk); break;
+                default: vkt::encode_block<false, false, false, 1>(tables, kp, lane, blk); break;
             }
             memcpy(out + 16 * b, blk, 16);
         }

@@ -16,7 +16,10 @@ ap.add_argument("--kind", type=int, default=0)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--uber", type=int, default=0)
 ap.add_argument("--fb", type=int, default=1)
+ap.add_argument("--lib", default=None, help="alternative libvierkant_bcn_cuda.so (tuning variants)")
 a = ap.parse_args()
+if a.lib:
+    capi._lib = capi.load_library(os.path.abspath(a.lib))
 img = synth.make_texture(a.size, a.size, a.kind)
 d_in = torch.from_numpy(img).cuda()
 d_out = torch.empty(((a.size // 4) ** 2, 16), dtype=torch.uint8, device="cuda")

@@ -57,7 +57,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: libvierkant_bcn_cuda.so cannot be built (and there is no CPU fallback)")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", CUDA_SO,
+    extra = os.environ.get("VKT_NVCC_EXTRA", "").split()  # tuning experiments only (e.g. -DVKT_BC7_THREADS=128)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", os.environ.get("VKT_CUDA_SO_OUT", CUDA_SO),
            os.path.join(CSRC, "bcn_cuda.cu"), os.path.join(CSRC, "bc7_tables.cpp")]
     if verbose:
         cmd.insert(1, "-Xptxas")

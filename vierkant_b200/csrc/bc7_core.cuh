@@ -73,8 +73,23 @@ VKT_FN int f2i(float a) { return __float2int_rz(a); }// operands are always satu
 VKT_FN float u64_to_f(uint64_t a) { return __ull2float_rn(a); }
 VKT_FN uint64_t f_to_u64(float a) { return __float2ull_rz(a); }
 VKT_FN int popc32(uint32_t m) { return __popc(m); }
+VKT_FN int ctz32(uint32_t m) { return __ffs(m) - 1; }
 // true if any lane of the currently converged group of the warp holds `p`
 VKT_FN bool warp_any(bool p) { return __ballot_sync(__activemask(), p) != 0u; }
+// Warp-cooperative helpers: only called where the whole warp is converged (see estimate_partition).
+constexpr uint32_t kWarpLanes = 32;
+VKT_FN uint32_t warp_lane() { return threadIdx.x & 31u; }
+VKT_FN uint32_t warp_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+VKT_FN uint64_t warp_min_u64(uint64_t v)
+{
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1)
+    {
+        const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        v = o < v ? o : v;
+    }
+    return v;
+}
 VKT_FN uint32_t dp4a_u8(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 VKT_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 VKT_FN uint32_t vmin_u16x2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
@@ -89,7 +104,12 @@ VKT_FN int f2i(float a) { return (int) a; }
 VKT_FN float u64_to_f(uint64_t a) { return (float) a; }
 VKT_FN uint64_t f_to_u64(float a) { return (uint64_t) a; }
 VKT_FN int popc32(uint32_t m) { return __builtin_popcount(m); }
+VKT_FN int ctz32(uint32_t m) { return __builtin_ctz(m); }
 VKT_FN bool warp_any(bool p) { return p; }
+constexpr uint32_t kWarpLanes = 1;// host emulation: a "warp" is one lane
+VKT_FN uint32_t warp_lane() { return 0; }
+VKT_FN uint32_t warp_ballot(bool p) { return p ? 1u : 0u; }
+VKT_FN uint64_t warp_min_u64(uint64_t v) { return v; }
 VKT_FN uint32_t dp4a_u8(uint32_t a, uint32_t b, uint32_t c)
 {
     return c + (a & 255) * (b & 255) + ((a >> 8) & 255) * ((b >> 8) & 255) + ((a >> 16) & 255) * ((b >> 16) & 255) + (a >> 24) * (b >> 24);
@@ -1119,18 +1139,29 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
     return total;
 }
 
-// estimate_partition, bc7enc.cpp:1754-1838.  Warp-uniform scan; `active` lanes want a result.
+// estimate_partition, bc7enc.cpp:1754-1838.  Must be called by the whole (converged) warp; `active` lanes want a result,
+// the others only lend their issue slots.
+//   iterations 0..34   warp-uniform scan: every lane scores the same partition for its own block; a ballot skips
+//                      candidates no lane of the batch needs (filterbank, bc7enc.cpp:1786-1799).
+//   iterations 35..63  only blocks whose best candidate after iteration 34 is the checkerboard (partition 34) go on
+//                      (bc7enc.cpp:1829-1830; ~2 % of blocks).  Scanning them warp-uniformly would make the whole warp pay
+//                      29 more candidates for one lane, so the warp turns around instead: the 29 candidates of ONE such
+//                      block are spread over the lanes (lane-varying partition, the block's column read by all lanes as
+//                      a shared-memory broadcast) and the winner is a (error, iteration) warp minimum -- the same
+//                      "first strictly smaller wins" the sequential scan implements.
 template<bool M7, bool PERC, bool KEY28, int STRIDE>
 VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool active)
 {
     const uint32_t total_partitions = umin(P.max_partitions, 64u);
     if(total_partitions <= 1) { return 0; }
+    constexpr uint32_t kUniformIters = 35;
+    const uint32_t uniform_end = umin(total_partitions, kUniformIters);
     uint64_t best_err = kNoErr;
     uint32_t best_partition = 0;
     uint32_t key = 0;
     bool running = active;
 #pragma unroll 1
-    for(uint32_t it = 0; it < total_partitions; ++it)
+    for(uint32_t it = 0; it < uniform_end; ++it)
     {
         const uint32_t part = VKT_UTAB(order)[it];
         running = running && (best_err > 0);// loop condition of the reference
@@ -1155,6 +1186,37 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
             if(err < best_err) { best_err = err, best_partition = part; }
             if((part == 34) && (best_partition != 34)) { running = false; }
             if(it == 13) { key = best_partition; }
+        }
+    }
+    if(total_partitions > kUniformIters)
+    {
+        running = running && (best_err > 0);
+        uint32_t pending = warp_ballot(running);
+        const uint32_t lane = warp_lane();
+#pragma unroll 1
+        while(pending)
+        {
+            const uint32_t src = (uint32_t) ctz32(pending);
+            pending &= pending - 1u;
+            const Lane<STRIDE> Ls{L.p + ((int) src - (int) lane)};// lane columns are consecutive records
+            uint64_t best_key = kNoErr;
+#pragma unroll 1
+            for(uint32_t base = kUniformIters; base < total_partitions; base += kWarpLanes)
+            {
+                const uint32_t it = base + lane;
+                if(it < total_partitions)
+                {
+                    const uint64_t err = estimate_pair<M7, PERC, KEY28, STRIDE>(T, P, Ls, VKT_UTAB(order)[it]);
+                    const uint64_t k = (err << 6) | (uint64_t) it;// err < 2^36: no overflow
+                    best_key = k < best_key ? k : best_key;
+                }
+            }
+            best_key = warp_min_u64(best_key);
+            if(lane == src)
+            {
+                const uint64_t err = best_key >> 6;
+                if(err < best_err) { best_err = err, best_partition = VKT_UTAB(order)[(uint32_t) best_key & 63u]; }
+            }
         }
     }
     return best_partition;
@@ -1274,21 +1336,19 @@ VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[
 
 // ---------------------------------------------------------------------------------------------------- two-subset modes
 // mode 1 (bc7enc.cpp:2336-2397) / mode 7 (bc7enc.cpp:2193-2259): estimate, fit both subsets, arbitrate.
+// Called by the whole converged warp; lanes with want == false only help the estimator.
 // Returns the weighted error, or kNoErr when not better than best_err.
 template<int MODE, bool PERC, bool KEY28, int STRIDE>
-VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint64_t best_err, BlockSolution &sol)
+VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool want, uint64_t best_err, BlockSolution &sol)
 {
     constexpr bool ALPHA = (MODE == 7);
-    const uint32_t part = estimate_partition<ALPHA, PERC, KEY28, STRIDE>(T, P, L, true);
+    const uint32_t part = estimate_partition<ALPHA, PERC, KEY28, STRIDE>(T, P, L, want);
+    if(!want) { return kNoErr; }
     const uint32_t mask = T.part2[part];
-    // element lists of the two subsets (ascending texel order, as the reference gathers them)
-    uint64_t perm0 = 0, perm1 = 0;
-    int n0 = 0, n1 = 0;
-    for(int i = 0; i < 16; ++i)
-    {
-        if((mask >> i) & 1u) { perm1 |= (uint64_t) i << (4 * n1++); }
-        else { perm0 |= (uint64_t) i << (4 * n0++); }
-    }
+    // element lists of the two subsets (ascending texel order, as the reference gathers them): nibble-packed work list
+    const int n0 = (int) T.est_n0[part], n1 = 16 - n0;
+    const uint64_t perm = T.est_perm[part];
+    const uint64_t perm0 = perm & ((1ull << (4 * n0)) - 1ull), perm1 = perm >> (4 * n0);// 1 <= n0 <= 15
     Cell c[2];
     const float mw = (MODE == 1) ? P.mode1_w : P.mode7_w;
     uint64_t trial = 0;
@@ -1413,16 +1473,23 @@ VKT_FN void prepare_lane(Lane<STRIDE> L)
     }
 }
 
-// bc7enc_compress_block (bc7enc.cpp:2402-2438) = handle_opaque_block (:2293-2400) | handle_alpha_block (:2139-2291).
-// L: the lane column with texels [0,16) filled; the YCbCr rows are filled here.
-template<bool PERC, bool KEY28, int STRIDE>
-VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
+// The dispatch of bc7enc_compress_block (bc7enc.cpp:2422-2437): does the block take the alpha path?
+VKT_FN bool block_has_alpha(const Bc7KernelParams &P, const uint32_t px[16])
 {
     uint32_t and_all = 0xFFFFFFFFu;
 #pragma unroll
-    for(int i = 0; i < 16; ++i) { and_all &= L.px(i); }
+    for(int i = 0; i < 16; ++i) { and_all &= px[i]; }
+    return P.force_alpha || ((and_all >> 24) != 255u);
+}
+
+// bc7enc_compress_block (bc7enc.cpp:2402-2438) after its dispatch: ALPHA == false is handle_opaque_block (:2293-2400),
+// ALPHA == true is handle_alpha_block (:2139-2291).  The caller classifies blocks first so that a warp only ever holds
+// blocks of one kind; the whole warp must call this converged (estimate_partition is warp-cooperative).
+// L: the lane column with texels [0,16) filled; the YCbCr part is filled here.
+template<bool PERC, bool KEY28, bool ALPHA, int STRIDE>
+VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
+{
     if(PERC) { prepare_lane<STRIDE>(L); }
-    const bool alpha = P.force_alpha || ((and_all >> 24) != 255u);
     const CellRef whole = {kIdentityPerm, 16};
 
     BlockSolution sol;
@@ -1431,28 +1498,22 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     sol.pbits[0] = sol.pbits[1] = 0;
     uint64_t best_err = kNoErr;
 
-    if(!alpha)
+    if(P.mode_mask & (1u << 6))
     {
-        if(P.mode_mask & (1u << 6))
-        {
-            Cell c6;
-            best_err = weigh(compress_cell<6, false, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
-            sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
-        }
-        if((best_err > 0) && (P.max_partitions > 0) && (P.mode_mask & (1u << 1)))
+        Cell c6;
+        best_err = weigh(compress_cell<6, ALPHA, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
+        sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
+    }
+    if(!ALPHA)
+    {
+        if((P.max_partitions > 0) && (P.mode_mask & (1u << 1)))// warp-uniform condition
         {
             BlockSolution s1 = sol;
-            if(two_subset_trial<1, PERC, KEY28, STRIDE>(T, P, L, best_err, s1) != kNoErr) { sol = s1; }
+            if(two_subset_trial<1, PERC, KEY28, STRIDE>(T, P, L, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
         }
     }
     else
     {
-        if(P.mode_mask & (1u << 6))
-        {
-            Cell c6;
-            best_err = weigh(compress_cell<6, true, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
-            sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
-        }
         if((best_err > 0) && (P.mode_mask & (1u << 5)))
         {
             uint32_t min_a = 255, max_a = 0;
@@ -1477,10 +1538,10 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
                 sol.pbits[0] = 0;
             }
         }
-        if((best_err > 0) && (P.mode_mask & (1u << 7)))
+        if(P.mode_mask & (1u << 7))// warp-uniform condition
         {
             BlockSolution s7 = sol;
-            if(two_subset_trial<7, PERC, KEY28, STRIDE>(T, P, L, best_err, s7) != kNoErr) { sol = s7; }
+            if(two_subset_trial<7, PERC, KEY28, STRIDE>(T, P, L, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
         }
     }
     pack_block(T, sol, out);

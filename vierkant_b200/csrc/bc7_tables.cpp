@@ -93,7 +93,11 @@ void bc7_tables_build(Bc7Tables *t)
         {
             for(uint32_t i = 0; i < 16; ++i)
             {
-                if(((k_part2[p] >> i) & 1u) == sub) { t->est_idx[p][n++] = static_cast<uint8_t>(i); }
+                if(((k_part2[p] >> i) & 1u) == sub)
+                {
+                    t->est_perm[p] |= static_cast<uint64_t>(i) << (4 * n);
+                    t->est_idx[p][n++] = static_cast<uint8_t>(i);
+                }
             }
             if(sub == 0) { t->est_n0[p] = static_cast<uint8_t>(n); }
         }

@@ -30,6 +30,7 @@ struct Bc7Tables
     uint8_t anchor2[64]; // bc7enc.cpp:94
     uint8_t order[64];   // partition scan order bc7enc.cpp:1765-1775
     // estimator work lists: texel indices of subset 0 (ascending) followed by those of subset 1, and |subset 0|
+    uint64_t est_perm[64];// the same list, one nibble per texel
     uint8_t est_idx[64][16];
     uint8_t est_n0[64];
 };

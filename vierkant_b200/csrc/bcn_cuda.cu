@@ -57,16 +57,82 @@ __device__ __forceinline__ void load_block_texels(const uint8_t *__restrict__ im
     }
 }
 
-// ------------------------------------------------------------------------------------------------ BC7 kernel
-constexpr int kBc7Threads = 256;
-constexpr int kBc7CtasPerSm = 3;// 3 x (64 KB lane columns + 8.4 KB tables) of shared memory, <= 80 registers per thread
+// ------------------------------------------------------------------------------------------------ BC7 kernels
+#ifndef VKT_BC7_THREADS
+#define VKT_BC7_THREADS 256
+#endif
+#ifndef VKT_BC7_CTAS
+#define VKT_BC7_CTAS 3
+#endif
+#ifndef VKT_BC7_CTAS_ALPHA
+#define VKT_BC7_CTAS_ALPHA 2
+#endif
+constexpr int kBc7Threads = VKT_BC7_THREADS;
+// Opaque blocks: 3 CTAs/SM = 3 x (64 KB lane columns + tables) of shared memory at <= 80 registers per thread.
+// Alpha blocks carry a fourth channel through every stage: 2 CTAs/SM at <= 128 registers (no spills) is faster.
+constexpr int kBc7CtasPerSm = VKT_BC7_CTAS, kBc7CtasPerSmAlpha = VKT_BC7_CTAS_ALPHA;
 
-template<bool PERC, bool KEY28, int NT>
-__global__ void __launch_bounds__(NT, kBc7CtasPerSm) bc7_encode_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks,
-                                                                        uint32_t comps, uint32_t stride, int vec16, const Bc7KernelParams P,
-                                                                        const Bc7Tables *__restrict__ g_tables, uint4 *__restrict__ out)
+// Stage 0: split the level's blocks into an opaque and an alpha work list (the dispatch of bc7enc_compress_block,
+// bc7enc.cpp:2422-2437), so that every warp of the encode kernels holds blocks of one kind.  counts[0] = #opaque,
+// counts[1] = #alpha.  List order is irrelevant to the output (block b always lands in out[b]); warp-aggregated
+// atomics keep it nearly sorted, so the encode kernels' texel loads stay coalesced.
+__global__ void __launch_bounds__(256) bc7_classify_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks,
+                                                            uint32_t stride, int vec16, uint32_t *__restrict__ counts,
+                                                            uint32_t *__restrict__ list_opaque, uint32_t *__restrict__ list_alpha)
+{
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = b < num_blocks;
+    bool alpha = false;
+    if(valid)
+    {
+        const uint32_t bx = b % blocks_x, by = b / blocks_x;
+        uint32_t and_all = 0xFFFFFFFFu;
+        if(vec16)
+        {
+#pragma unroll
+            for(int y = 0; y < 4; ++y)
+            {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + size_t(by * 4 + y) * stride) + bx);
+                and_all &= v.x & v.y & v.z & v.w;
+            }
+        }
+        else
+        {
+            for(int y = 0; y < 4; ++y)
+            {
+                const uint8_t *row = img + size_t(by * 4 + y) * stride + size_t(bx) * 16;
+                for(int x = 0; x < 4; ++x) { and_all &= uint32_t(row[4 * x + 3]) << 24; }
+            }
+        }
+        alpha = (and_all >> 24) != 255u;
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m_alpha = __ballot_sync(0xFFFFFFFFu, valid && alpha), m_opaque = __ballot_sync(0xFFFFFFFFu, valid && !alpha);
+    uint32_t base_a = 0, base_o = 0;
+    if(lane == 0)
+    {
+        if(m_opaque) { base_o = atomicAdd(&counts[0], __popc(m_opaque)); }
+        if(m_alpha) { base_a = atomicAdd(&counts[1], __popc(m_alpha)); }
+    }
+    base_o = __shfl_sync(0xFFFFFFFFu, base_o, 0), base_a = __shfl_sync(0xFFFFFFFFu, base_a, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if(valid)
+    {
+        if(alpha) { list_alpha[base_a + __popc(m_alpha & below)] = b; }
+        else { list_opaque[base_o + __popc(m_opaque & below)] = b; }
+    }
+}
+
+// One lane == one block of the work list (list == nullptr: every block of the level, in order).
+template<bool PERC, bool KEY28, bool ALPHA, int NT>
+__global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm)
+        bc7_encode_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks, uint32_t comps, uint32_t stride, int vec16,
+                          const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables, const uint32_t *__restrict__ list,
+                          const uint32_t *__restrict__ count, uint4 *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
+    const uint32_t n = count ? __ldg(count) : num_blocks;
+    if(blockIdx.x * NT >= n) { return; }// the grid is sized for the whole level; lists are usually shorter
     Bc7Tables &s_tables = *reinterpret_cast<Bc7Tables *>(s_raw);
     Texel *s_lane = reinterpret_cast<Texel *>(s_raw + sizeof(Bc7Tables));// one 16-record column per lane (see Lane<>)
     {
@@ -74,25 +140,35 @@ __global__ void __launch_bounds__(NT, kBc7CtasPerSm) bc7_encode_kernel(const uin
         uint4 *dst = reinterpret_cast<uint4 *>(&s_tables);
         for(uint32_t i = threadIdx.x; i < sizeof(Bc7Tables) / 16; i += NT) { dst[i] = __ldg(src + i); }
     }
-    const uint32_t b = blockIdx.x * NT + threadIdx.x;
-    const uint32_t bb = min(b, num_blocks - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    const uint32_t ii = min(i, n - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
+    const uint32_t b = list ? __ldg(list + ii) : ii;
     Lane<NT> lane{s_lane + threadIdx.x};
-    load_block_texels<NT>(img, comps, stride, vec16 != 0, bb % blocks_x, bb / blocks_x, lane.p);
+    load_block_texels<NT>(img, comps, stride, vec16 != 0, b % blocks_x, b / blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, KEY28, NT>(s_tables, P, lane, blk);
-    if(b < num_blocks) { out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
+    encode_block<PERC, KEY28, ALPHA, NT>(s_tables, P, lane, blk);
+    if(i < n) { out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Tables) + size_t(kBc7Threads) * 16 * sizeof(Texel);
 
+template<bool PERC, bool KEY28, bool ALPHA>
+static cudaError_t bc7_kernel_attribute()
+{
+    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
+}
 // > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
 static cudaError_t bc7_kernel_attributes()
 {
-    cudaError_t e = cudaFuncSetAttribute(bc7_encode_kernel<true, true, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
-    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<true, false, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
-    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<false, true, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
-    if(e == cudaSuccess) { e = cudaFuncSetAttribute(bc7_encode_kernel<false, false, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes)); }
+    cudaError_t e = bc7_kernel_attribute<true, true, false>();
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, true>(); }
     return e;
 }
 
@@ -148,6 +224,8 @@ static int fail(vkt_bcn_ctx *ctx, int code, const char *fmt, ...)
         }                                                                                                                      \
     } while(0)
 
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 static int ensure(vkt_bcn_ctx *ctx, void **ptr, size_t *cap, size_t need)
 {
     if(*cap >= need) { return VKT_BCN_OK; }
@@ -197,22 +275,53 @@ static int launch_bc7(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_
     const uint32_t bx = w / 4, nblocks = bx * (h / 4);
     const int vec16 = (comps == 4) && ((stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_px) & 15u) == 0);
     const uint32_t grid = (nblocks + kBc7Threads - 1) / kBc7Threads;
-    auto go = [&](auto kernel) {
-        kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(static_cast<const uint8_t *>(d_px), bx, nblocks, comps, stride, vec16, kp,
-                                                           s->d_tables, static_cast<uint4 *>(d_out));
+    const uint8_t *px = static_cast<const uint8_t *>(d_px);
+    uint4 *outp = static_cast<uint4 *>(d_out);
+    auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
+        auto go = [&](auto kernel) {
+            kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(px, bx, nblocks, comps, stride, vec16, kp, s->d_tables, list, cnt, outp);
+        };
+        const int sel = (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+        switch(sel)
+        {
+            case 7: go(bc7_encode_kernel<true, true, true, kBc7Threads>); break;
+            case 6: go(bc7_encode_kernel<true, true, false, kBc7Threads>); break;
+            case 5: go(bc7_encode_kernel<true, false, true, kBc7Threads>); break;
+            case 4: go(bc7_encode_kernel<true, false, false, kBc7Threads>); break;
+            case 3: go(bc7_encode_kernel<false, true, true, kBc7Threads>); break;
+            case 2: go(bc7_encode_kernel<false, true, false, kBc7Threads>); break;
+            case 1: go(bc7_encode_kernel<false, false, true, kBc7Threads>); break;
+            default: go(bc7_encode_kernel<false, false, false, kBc7Threads>); break;
+        }
     };
-    if(params->perceptual)
+    if(kp.force_alpha)
     {
-        if(kp.key28) { go(bc7_encode_kernel<true, true, kBc7Threads>); }
-        else { go(bc7_encode_kernel<true, false, kBc7Threads>); }
+        encode(true, nullptr, nullptr);
+        count(ctx, 1, 0, 0);
+    }
+    else if(comps == 3)
+    {
+        encode(false, nullptr, nullptr);// get_block injects alpha = 255: every block is opaque
+        count(ctx, 1, 0, 0);
     }
     else
     {
-        if(kp.key28) { go(bc7_encode_kernel<false, true, kBc7Threads>); }
-        else { go(bc7_encode_kernel<false, false, kBc7Threads>); }
+        // stream-ordered scratch: [counts: 2 x u32, padded to 256 B][opaque list][alpha list]
+        uint8_t *scratch = nullptr;
+        const size_t list_bytes = align_up(size_t(nblocks) * sizeof(uint32_t), 256);
+        VKT_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), 256 + 2 * list_bytes, stream));
+        uint32_t *counts = reinterpret_cast<uint32_t *>(scratch);
+        uint32_t *list_o = reinterpret_cast<uint32_t *>(scratch + 256), *list_a = reinterpret_cast<uint32_t *>(scratch + 256 + list_bytes);
+        VKT_CUDA(ctx, cudaMemsetAsync(counts, 0, 8, stream));
+        bc7_classify_kernel<<<(nblocks + 255) / 256, 256, 0, stream>>>(px, bx, nblocks, stride, vec16, counts, list_o, list_a);
+        encode(false, list_o, counts);
+        encode(true, list_a, counts + 1);
+        const cudaError_t e = cudaGetLastError();
+        VKT_CUDA(ctx, cudaFreeAsync(scratch, stream));
+        VKT_CUDA(ctx, e);
+        count(ctx, 3, 0, 0);
     }
     VKT_CUDA(ctx, cudaGetLastError());
-    count(ctx, 1, 0, 0);
     return VKT_BCN_OK;
 }
 
@@ -255,8 +364,6 @@ static int encode_rows_async(vkt_bcn_ctx *ctx, DeviceSlot *s, uint32_t mode, con
     count(ctx, 0, in_bytes, out_bytes);
     return VKT_BCN_OK;
 }
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }// namespace vkt
 
@@ -309,6 +416,15 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
         if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
         if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
+        if(e == cudaSuccess)
+        {
+            // the per-launch work lists come from the stream-ordered allocator: keep freed blocks cached in the pool
+            // instead of returning them to the driver at every synchronisation
+            cudaMemPool_t pool = nullptr;
+            e = cudaDeviceGetDefaultMemPool(&pool, dev);
+            uint64_t keep = ~0ull;
+            if(e == cudaSuccess) { e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+        }
         if(e != cudaSuccess)
         {
             fail(nullptr, VKT_BCN_ERR_CUDA, "device %d initialisation failed: %s", dev, cudaGetErrorString(e));
