@@ -53,9 +53,12 @@ void port_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const port_b
 /* Decoder for the modes bc7enc emits (1, 5, 6, 7) plus the remaining BC7 modes; used for the PSNR fallback metric. */
 void port_bc7_unpack_blocks(const uint8_t *blocks, uint64_t num_blocks, uint8_t *px);
 
-/* Implemented in bc5_oracle.c / stbir_oracle.c */
+/* Implemented in bc5_oracle.c / stbir_oracle.c / compress_oracle.c */
 void port_bc5_encode_blocks(const uint8_t *px, uint64_t num_blocks, uint8_t *out);
 void port_resize_u8(const uint8_t *in, uint32_t w, uint32_t h, uint32_t comps, uint8_t *out, uint32_t ow, uint32_t oh);
+uint32_t port_compress_num_levels(uint32_t width, uint32_t height, int mipmaps);
+uint32_t port_compress(const uint8_t *img, uint32_t width, uint32_t height, uint32_t comps, uint32_t mode, int mipmaps,
+                       const port_bc7_params *params, uint8_t *const *level_blocks, int threads);
 
 #ifdef __cplusplus
 }

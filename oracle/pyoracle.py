@@ -188,3 +188,28 @@ class RefOracle(_BlockOracle):
 class PortOracle(_BlockOracle):
     prefix = "port_"
     path = PORT_SO
+
+    def __init__(self):
+        super().__init__()
+        L = self.lib
+        L.port_compress_num_levels.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.port_compress_num_levels.restype = C.c_uint32
+        L.port_compress.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                    C.POINTER(Bc7Params), C.POINTER(C.c_void_p), C.c_int]
+        L.port_compress.restype = C.c_uint32
+
+    def compress(self, img: np.ndarray, mode: int = 1, mipmaps: bool = False, threads: int = 1,
+                 params: Bc7Params | None = None) -> dict:
+        """Restatement of vierkant::bcn::compress() (oracle/compress_oracle.c); same result layout as RefOracle.compress."""
+        img, ptr = _u8(img)
+        h, w, c = img.shape
+        r4 = lambda v: (v + 3) & ~3
+        n = int(self.lib.port_compress_num_levels(w, h, int(mipmaps)))
+        lw, lh, levels = r4(w), r4(h), []
+        for _ in range(n):
+            levels.append(np.zeros(((lw // 4) * (lh // 4), 16), dtype=np.uint8))
+            lw, lh = r4(max(lw // 2, 1)), r4(max(lh // 2, 1))
+        ptrs = (C.c_void_p * n)(*[l.ctypes.data for l in levels])
+        pp = C.byref(params) if params is not None else None
+        self.lib.port_compress(ptr, w, h, c, mode, int(mipmaps), pp, ptrs, threads)
+        return {"mode": mode, "base_width": r4(w), "base_height": r4(h), "levels": levels}

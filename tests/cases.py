@@ -25,6 +25,9 @@ PARAM_CASES = {
     "pbit1_weight": dict(pbit1_weight=1.5),
     "mode_weights": dict(mode1_error_weight=0.9, mode6_error_weight=1.1, mode5_error_weight=1.2, mode7_error_weight=0.8),
     "bias_mode1_pbits": dict(bias_mode1_pbits=1),
+    # per-texel errors above 2^28 (but below 2^31): the kernels' packed 28-bit argmin keys must not be used
+    "big_weights": dict(weights=[800, 400, 100, 200]),
+    "big_weights_linear": dict(perceptual=0, weights=[9000, 7000, 5000, 6000]),
 }
 # accepted by the oracles only (the C ABI returns VKT_BCN_ERR_UNSUPPORTED)
 ORACLE_ONLY_CASES = {

@@ -71,3 +71,59 @@ def test_known_answer_uber4(port_oracle, known):
     img = synth.make_texture(entry["size"], entry["size"], entry["kind"])
     b = port_oracle.encode_blocks(synth.to_blocks(img), default_params(**entry["params"]), threads=os.cpu_count() or 1)
     assert "%016x" % synth.fnv1a64_words(b) == entry["fnv1a64"]
+
+
+# ---------------------------------------------------------------------------------------------------- resize / BC5 / chain
+RESIZE_SHAPES = [(64, 64, 64, 64, 4), (64, 64, 32, 32, 4), (123, 81, 124, 84, 4), (256, 128, 16, 8, 4), (60, 36, 60, 36, 3),
+                 (4, 4, 512, 256, 4), (100, 52, 52, 28, 4), (124, 84, 64, 44, 4), (8, 4, 4, 4, 4), (4, 4, 4, 4, 4), (12, 20, 8, 12, 3),
+                 (33, 7, 36, 8, 1), (50, 50, 200, 30, 2), (17, 300, 20, 150, 4), (640, 8, 320, 4, 4)]
+
+
+def _bytes_hash(a):
+    return "%016x" % synth.fnv1a64_words(np.frombuffer(a.tobytes() + b"\0" * (-a.size % 8), dtype=np.uint8))
+
+
+def test_port_resize_matches_golden(port_oracle, known):
+    for e in known["resize"]:
+        img = synth.make_texture(e["w"], e["h"], e["kind"])[..., : e["comps"]]
+        assert _bytes_hash(port_oracle.resize(img, e["ow"], e["oh"])) == e["fnv1a64_bytes"], e
+
+
+@pytest.mark.parametrize("w,h,ow,oh,c", RESIZE_SHAPES)
+def test_port_resize_matches_ref(port_oracle, ref_oracle, w, h, ow, oh, c):
+    img = synth.make_texture(w, h, 1, seed=w * 7 + h)[..., :c]
+    assert np.array_equal(port_oracle.resize(img, ow, oh), ref_oracle.resize(img, ow, oh))
+
+
+def test_port_bc5_matches_golden_and_ref(port_oracle, ref_oracle, golden):
+    assert np.array_equal(port_oracle.encode_bc5_blocks(golden["tiles"]), golden["bc5_blocks"])
+    tiles = edge_tiles(31, 50)
+    assert np.array_equal(port_oracle.encode_bc5_blocks(tiles), ref_oracle.encode_bc5_blocks(tiles))
+
+
+def test_port_compress_matches_reference_test_shapes(port_oracle, known):
+    """The five shapes of the reference's tests/TestCompressionBC7.cpp, against hashes taken from the reference."""
+    for e in known["reference_tests"]:
+        img = port_oracle.resize(synth.checkerboard_4x4(e["comps"]), e["w"], e["h"])
+        r = port_oracle.compress(img, e["mode"], e["mips"], threads=os.cpu_count() or 1)
+        assert [r["base_width"], r["base_height"]] == e["base"]
+        assert [int(l.shape[0]) for l in r["levels"]] == e["level_blocks"]
+        allb = np.concatenate(r["levels"])
+        assert "%016x" % synth.fnv1a64_words(allb) == e["fnv1a64"], e["name"]
+
+
+@pytest.mark.parametrize("w,h,c,mode,mips", [(100, 60, 4, 1, True), (64, 64, 3, 1, True), (36, 20, 4, 0, True), (5, 3, 4, 1, True)])
+def test_port_compress_matches_ref(port_oracle, ref_oracle, w, h, c, mode, mips):
+    img = synth.make_texture(w, h, 1, seed=w + h)[..., :c]
+    a, b = port_oracle.compress(img, mode, mips, threads=4), ref_oracle.compress(img, mode, mips, 0)
+    assert (a["base_width"], a["base_height"], len(a["levels"])) == (b["base_width"], b["base_height"], len(b["levels"]))
+    for x, y in zip(a["levels"], b["levels"]):
+        assert np.array_equal(x, y)
+
+
+def test_port_compress_known_answer_1024(port_oracle, known):
+    e = known["compress"][0]
+    r = port_oracle.compress(synth.make_texture(e["size"], e["size"], e["kind"]), 1, True, threads=os.cpu_count() or 1)
+    allb = np.concatenate(r["levels"])
+    assert (len(r["levels"]), allb.shape[0]) == (e["levels"], e["blocks"])
+    assert "%016x" % synth.fnv1a64_words(allb) == e["fnv1a64"]
