@@ -11,6 +11,7 @@
 
 #include "../../vierkant_b200/csrc/bc7_core.cuh"
 #include "../../vierkant_b200/csrc/bc7_params.h"
+#include "../../vierkant_b200/csrc/resize_axis.h"
 
 extern "C" {
 
@@ -63,6 +64,44 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
             pool.emplace_back(work, num_blocks * t / threads, num_blocks * (t + 1) / threads);
         }
         for(auto &t: pool) { t.join(); }
+    }
+    return 0;
+}
+
+// The product's host-built tap lists (resize_axis.h) evaluated on the CPU in the order the two CUDA passes use.
+int emul_resize_u8(const uint8_t *in, uint32_t w, uint32_t h, uint32_t comps, uint8_t *out, uint32_t ow, uint32_t oh)
+{
+    vkt::ResizeAxis ax, ay;
+    ax.build((int) w, (int) ow);
+    ay.build((int) h, (int) oh);
+    const size_t row = size_t(ow) * comps;
+    std::vector<float> band(size_t(h) * row, 0.0f);
+    for(uint32_t r = 0; r < h; ++r)
+    {
+        for(uint32_t x = 0; x < ow; ++x)
+        {
+            for(uint32_t c = 0; c < comps; ++c)
+            {
+                float acc = 0.0f;
+                for(int t = ax.start[x]; t < ax.start[x + 1]; ++t)
+                {
+                    acc = acc + (((float) in[(size_t(r) * w + size_t(ax.idx[size_t(t)])) * comps + c]) / 255.0f) * ax.coef[size_t(t)];
+                }
+                band[size_t(r) * row + size_t(x) * comps + c] = acc;
+            }
+        }
+    }
+    for(uint32_t y = 0; y < oh; ++y)
+    {
+        for(size_t i = 0; i < row; ++i)
+        {
+            float acc = 0.0f;
+            for(int t = ay.start[y]; t < ay.start[y + 1]; ++t) { acc = acc + band[size_t(ay.idx[size_t(t)]) * row + i] * ay.coef[size_t(t)]; }
+            float f = acc < 0.0f ? 0.0f : (acc > 1.0f ? 1.0f : acc);
+            const float s = f * 255.0f;
+            const int q = (int) s;
+            out[size_t(y) * row + i] = (uint8_t) (q + ((s - (float) q) >= 0.5f ? 1 : 0));
+        }
     }
     return 0;
 }

@@ -1,0 +1,101 @@
+"""GPU parity of the rows around the block encoder (SURVEY.md 8f N1/N2 and the 8b boundary): stbir-exact resize, BC5,
+and the whole vierkant::bcn::compress() chain through the C ABI.  Bit-exact against the oracle and the reference-derived
+golden hashes (tests/golden/known_answers.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import edge_tiles, tiles_to_image
+from vierkant_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+RESIZE_SHAPES = [(64, 64, 64, 64, 4), (64, 64, 32, 32, 4), (123, 81, 124, 84, 4), (256, 128, 16, 8, 4), (60, 36, 60, 36, 3),
+                 (4, 4, 512, 256, 4), (100, 52, 52, 28, 4), (124, 84, 64, 44, 4), (8, 4, 4, 4, 4), (4, 4, 4, 4, 4), (12, 20, 8, 12, 3),
+                 (33, 7, 36, 8, 1), (50, 50, 200, 30, 2), (17, 300, 20, 150, 4), (640, 8, 320, 4, 4), (1000, 4, 3, 4, 4)]
+
+
+@pytest.fixture(scope="module")
+def known():
+    with open(os.path.join(GOLD, "known_answers.json")) as f:
+        return json.load(f)
+
+
+def _bytes_hash(a):
+    return "%016x" % synth.fnv1a64_words(np.frombuffer(a.tobytes() + b"\0" * (-a.size % 8), dtype=np.uint8))
+
+
+@pytest.mark.parametrize("w,h,ow,oh,c", RESIZE_SHAPES)
+def test_resize_matches_oracle(ctx, port_oracle, w, h, ow, oh, c):
+    img = synth.make_texture(w, h, 1, seed=3 * w + h)[..., :c]
+    assert np.array_equal(ctx.resize_u8(img, ow, oh), port_oracle.resize(img, ow, oh))
+
+
+def test_resize_matches_reference_hashes(ctx, known):
+    for e in known["resize"]:
+        img = synth.make_texture(e["w"], e["h"], e["kind"])[..., : e["comps"]]
+        assert _bytes_hash(ctx.resize_u8(img, e["ow"], e["oh"])) == e["fnv1a64_bytes"], e
+
+
+def test_resize_large_is_banded_and_exact(ctx, port_oracle):
+    """2048 x 1024 -> 1024 x 512 and the 1:1 Mitchell pass (level 0 of every chain)."""
+    img = synth.make_texture(2048, 1024, 0, seed=9)
+    assert np.array_equal(ctx.resize_u8(img, 1024, 512), port_oracle.resize(img, 1024, 512))
+    assert np.array_equal(ctx.resize_u8(img, 2048, 1024), port_oracle.resize(img, 2048, 1024))
+
+
+def test_bc5_matches_golden_and_oracle(ctx, port_oracle):
+    golden = np.load(os.path.join(GOLD, "bc7_blocks.npz"))
+    tiles = golden["tiles"]
+    n = tiles.shape[0]
+    pad = (-n) % 8
+    t = np.concatenate([tiles, np.repeat(tiles[-1:], pad, axis=0)]) if pad else tiles
+    assert np.array_equal(ctx.encode_bc5(tiles_to_image(t, 8))[:n], golden["bc5_blocks"])
+    tiles = edge_tiles(41, 64)
+    assert np.array_equal(ctx.encode_bc5(tiles_to_image(tiles, 32)), port_oracle.encode_bc5_blocks(tiles))
+    rgb = np.ascontiguousarray(tiles_to_image(tiles, 32)[..., :3])
+    assert np.array_equal(ctx.encode_bc5(rgb), port_oracle.encode_bc5_blocks(tiles))
+
+
+def test_compress_reference_test_shapes(ctx, port_oracle, known):
+    """The five cases of the reference's tests/TestCompressionBC7.cpp: shapes as its check() asserts them, bytes as the
+    reference itself produced them."""
+    for e in known["reference_tests"]:
+        img = port_oracle.resize(synth.checkerboard_4x4(e["comps"]), e["w"], e["h"])
+        plan, levels = ctx.compress(img, e["mode"], e["mips"])
+        assert [plan.base_width, plan.base_height] == e["base"]
+        assert [int(l.shape[0]) for l in levels] == e["level_blocks"]
+        assert "%016x" % synth.fnv1a64_words(np.concatenate(levels)) == e["fnv1a64"], e["name"]
+
+
+@pytest.mark.parametrize("w,h,c,mode,mips", [(100, 60, 4, 1, True), (64, 64, 3, 1, True), (36, 20, 4, 0, True), (5, 3, 4, 1, True),
+                                             (256, 256, 4, 1, False), (4, 4, 4, 1, True), (260, 12, 4, 1, True)])
+def test_compress_matches_oracle(ctx, port_oracle, w, h, c, mode, mips):
+    img = synth.make_texture(w, h, 1, seed=w + h)[..., :c]
+    want = port_oracle.compress(img, mode, mips, threads=os.cpu_count() or 1)
+    plan, levels = ctx.compress(img, mode, mips)
+    assert (plan.base_width, plan.base_height, plan.num_levels) == (want["base_width"], want["base_height"], len(want["levels"]))
+    for got, ref in zip(levels, want["levels"]):
+        assert np.array_equal(got, ref)
+
+
+def test_compress_known_answers(ctx, known):
+    """BASELINE configs[0]: 1024^2 (and 2048^2) synthetic textures + full chain, hashes from the reference's compress()."""
+    for e in known["compress"]:
+        plan, levels = ctx.compress(synth.make_texture(e["size"], e["size"], e["kind"]), capi.MODE_BC7, True)
+        allb = np.concatenate(levels)
+        assert (plan.num_levels, allb.shape[0]) == (e["levels"], e["blocks"])
+        assert "%016x" % synth.fnv1a64_words(allb) == e["fnv1a64"], e
+
+
+def test_compress_with_parameters(ctx, port_oracle):
+    from oracle.pyoracle import default_params
+    img = synth.make_texture(128, 64, 1, seed=12)
+    kw = dict(uber_level=2, mode17_partition_estimation_filterbank=0)
+    want = port_oracle.compress(img, 1, True, threads=os.cpu_count() or 1, params=default_params(**kw))
+    _, levels = ctx.compress(img, capi.MODE_BC7, True, capi.default_params(**kw))
+    for got, ref in zip(levels, want["levels"]):
+        assert np.array_equal(got, ref)

@@ -19,6 +19,7 @@ def emul():
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "host_emul")], check=True)
     lib = C.CDLL(os.path.join(HERE, "host_emul", "libvkt_emul.so"))
     lib.emul_bc7_encode_blocks.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(Bc7Params), C.POINTER(C.c_uint8), C.c_int]
+    lib.emul_resize_u8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
 
     def encode(tiles, params):
         tiles = np.ascontiguousarray(tiles, dtype=np.uint8)
@@ -27,6 +28,14 @@ def emul():
         rc = lib.emul_bc7_encode_blocks(tiles.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.byref(params),
                                         out.ctypes.data_as(C.POINTER(C.c_uint8)), 4)
         return rc, out
+
+    def resize(img, ow, oh):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w, c = img.shape
+        out = np.zeros((oh, ow, c), dtype=np.uint8)
+        assert lib.emul_resize_u8(img.ctypes.data, w, h, c, out.ctypes.data, ow, oh) == 0
+        return out
+    encode.resize = resize
     return encode
 
 
@@ -43,3 +52,16 @@ def test_device_logic_matches_oracle(emul, port_oracle, case):
 def test_unsupported_knobs_are_rejected(emul, kw):
     rc, _ = emul(edge_tiles(1, 1), default_params(**kw))
     assert rc == -2
+
+
+RESIZE_SHAPES = [(64, 64, 64, 64, 4), (64, 64, 32, 32, 4), (123, 81, 124, 84, 4), (256, 128, 16, 8, 4), (60, 36, 60, 36, 3),
+                 (4, 4, 512, 256, 4), (100, 52, 52, 28, 4), (124, 84, 64, 44, 4), (8, 4, 4, 4, 4), (4, 4, 4, 4, 4), (12, 20, 8, 12, 3),
+                 (33, 7, 36, 8, 1), (50, 50, 200, 30, 2), (17, 300, 20, 150, 4), (640, 8, 320, 4, 4), (1024, 16, 512, 8, 4),
+                 (2048, 4, 2048, 4, 4), (1000, 4, 3, 4, 4)]
+
+
+@pytest.mark.parametrize("w,h,ow,oh,c", RESIZE_SHAPES)
+def test_resize_tap_lists_match_oracle(emul, port_oracle, w, h, ow, oh, c):
+    """The per-output tap lists the CUDA resize passes consume (resize_axis.h), evaluated on the CPU in kernel order."""
+    img = synth.make_texture(w, h, 1, seed=3 * w + h)[..., :c]
+    assert np.array_equal(emul.resize(img, ow, oh), port_oracle.resize(img, ow, oh))

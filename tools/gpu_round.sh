@@ -15,7 +15,7 @@ echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
 timeout 300 python tools/prof_target.py --launches 5 > gpurun_out/${TAG}_kernel_ms.txt 2>&1; cat gpurun_out/${TAG}_kernel_ms.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:bc7_encode -s 1 -c 1 -f -o gpurun_out/${TAG}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bc7_encode -s 2 -c 1 -f -o gpurun_out/${TAG}_prof \
     python tools/prof_target.py --launches 2 > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu exit $?"
 ls -la gpurun_out

@@ -173,8 +173,13 @@ static cudaError_t bc7_kernel_attributes()
 }
 
 // ------------------------------------------------------------------------------------------------ context
+}// namespace vkt
+struct vkt_axis_cache;// resize_core.cuh
+namespace vkt
+{
 struct DeviceSlot
 {
+    vkt_axis_cache *axis_cache = nullptr;
     int device = -1;
     cudaStream_t stream = nullptr;
     Bc7Tables *d_tables = nullptr;
@@ -452,6 +457,7 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
             cudaFree(s->d_in);
             cudaFree(s->d_out);
             cudaFree(s->d_tmp);
+            delete s->axis_cache;// frees the cached resize tables
         }
         delete s;
     }
