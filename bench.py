@@ -11,8 +11,11 @@ data path; weak scaling) and `value` is the whole-job pixel rate over the max-ov
 
   value  : all mip levels already resident in HBM, only our kernels inside the timed region (CUDA events on the
            launching stream).  Four different textures are rotated so the inputs of consecutive steps (358 MB) exceed L2.
-  e2e    : the same chain through the host-buffer C-ABI call (vkt_bcn_cuda_encode_batch): pinned host level images
-           in, pinned host blocks out, H2D + kernels + D2H inside the timed region.
+  e2e    : the reference-facing call itself, vkt_bcn_cuda_compress == vierkant::bcn::compress(): the 4096x4096 source
+           image in pinned host memory in, every level's blocks in pinned host memory out; H2D of the source, the
+           stbir-exact resize chain (level 0 included, as the reference does), classification, encode kernels and D2H
+           of the blocks are all inside the timed region.  This is what the reference arm (--impl reference, the
+           reference's compress() with stbir on the host cores) is compared with.
   roofline     : ALU/issue-slot bound: algorithmic lane-ops per launch / kernel time vs a peak
                  microbenchmarked in this run; HBM GB/s alongside (informational).
   cpu_baseline : the reference (oracle/_ref, unmodified sources) or the C port, on a bounded sample, on rank 0 at N=1.
@@ -241,14 +244,19 @@ def main():
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
 
+    dev_batches = [ctx.make_device_batch([(t, w, h, 4) for t, (w, h) in zip(lv, dims)], dev_out) for lv in dev_levels]
+
     def step_device(i):
-        lv = dev_levels[i % ROTATE]
-        for (w, h), src, dst in zip(dims, lv, dev_out):
-            ctx.encode_bc7_device(src, w, h, 4, dst, params, 0, stream)
+        # all 11 levels of the chain in one call: one classify + two encode launches (vkt_bcn_cuda_encode_batch_device)
+        ctx.encode_batch_device(capi.MODE_BC7, dev_batches[i % ROTATE], params, 0, stream)
+
+    import ctypes as C
+    out_ptrs = (C.c_void_p * len(dims))(*[t.data_ptr() for t in host_out])
 
     def step_e2e(i):
-        lv = host_levels[i % ROTATE]
-        ctx.encode_batch(capi.MODE_BC7, [(t.data_ptr(), w, h, 4) for t, (w, h) in zip(lv, dims)], host_out, params)
+        src = host_levels[i % ROTATE][0]  # the level-0 texture is the source image of the chain
+        ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                 C.byref(params), out_ptrs))
 
     def barrier():
         if world > 1:
@@ -315,6 +323,10 @@ def main():
         # issue-slot peak: SMs x 4 schedulers x 32 lanes x clock, at the max SM clock (conservative
         # denominator) -- replaced by the microbenchmarked figure when the library provides one
         alu_peak = props.multi_processor_count * 4 * 32 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        try:
+            probe = ctx.measure_issue_peak(0)
+        except Exception:
+            probe = None
         l0_pix = dims[0][0] * dims[0][1]
         achieved = l0_pix * OPS_PER_PIXEL / (kernel_ms * 1e-3)
         line = {
@@ -327,7 +339,8 @@ def main():
                        "params": "bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
-                    "api": "vkt_bcn_cuda_encode_batch (pinned host level images in, pinned host blocks out)"},
+                    "api": "vkt_bcn_cuda_compress == vierkant::bcn::compress(): pinned host source image in, stbir-exact resize chain + "
+                           "classify + encode on the GPU, pinned host blocks of all levels out"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",
@@ -336,6 +349,8 @@ def main():
                          "ops_per_pixel": OPS_PER_PIXEL,
                          "peak_source": f"{props.multi_processor_count} SMs x 4 x 32 lanes x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peak_src} clock)",
                          "sm_mhz_during_run": sm_mhz,
+                         "issue_probe_tlaneops": None if probe is None else probe * 1e-12,
+                         "frac_of_probe": None if not probe else achieved / probe,
                          "hbm": {"achieved_gbs": l0_pix * BYTES_PER_PIXEL / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": f"informational, {peak_src}"}},
         }

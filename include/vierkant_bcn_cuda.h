@@ -119,6 +119,12 @@ int vkt_bcn_cuda_encode_bc7_device(vkt_bcn_ctx *ctx, int slot, const void *d_pix
 int vkt_bcn_cuda_encode_bc5_device(vkt_bcn_ctx *ctx, int slot, const void *d_pixels, uint32_t width, uint32_t height,
                                    uint32_t comps, uint32_t row_stride_bytes, void *d_out_blocks, void *cuda_stream);
 
+/* Several device-resident images (all levels of a chain, all textures of a material) in one go: every 16 images share
+ * ONE set of kernel launches, so a tail of tiny mip levels costs nothing extra.  images[i].pixels / .out_blocks are
+ * device pointers on slot `slot`; stream semantics as above. */
+int vkt_bcn_cuda_encode_batch_device(vkt_bcn_ctx *ctx, int slot, uint32_t mode, const vkt_bcn_image *images,
+                                     uint32_t num_images, const vkt_bc7_params *params, void *cuda_stream);
+
 /* crocore::Image_<uint8_t>::resize == stbir_resize_uint8 with its defaults (extern/crocore/src/Image.cpp:239-247),
  * bit-exact, on the GPU.  Host in / host out, tightly packed, comps 1..4. */
 int vkt_bcn_cuda_resize_u8(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
@@ -146,6 +152,11 @@ typedef struct vkt_bcn_stats
     uint64_t d2h_bytes;
 } vkt_bcn_stats;
 int vkt_bcn_cuda_get_stats(const vkt_bcn_ctx *ctx, vkt_bcn_stats *out);
+
+
+/* Measurement support: sustained issue rate of the device's integer pipes in lane-operations per second (a short
+ * probe kernel with a balanced FMA-pipe / ALU-pipe mix), the denominator of the ALU roofline bench.py reports. */
+int vkt_bcn_cuda_measure_issue_peak(vkt_bcn_ctx *ctx, int slot, double *lane_ops_per_second);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,91 @@
+// texture_block_compression_cuda.cpp -- drop-in translation unit for vierkant: vierkant::bcn::compress() on B200.
+//
+// Replaces /root/reference/src/texture_block_compression.cpp when vierkant is configured with -DVIERKANT_BCN_CUDA=ON
+// (integration/vierkant_bcn_cuda.cmake).  Same signature, same compress_info_t / compress_result_t contract
+// (include/vierkant/texture_block_compression.hpp:15-52), identical block bytes and mip chains; the work itself is done
+// by libvierkant_bcn_cuda through its C ABI (include/vierkant_bcn_cuda.h).  There is no CPU fallback: if no CUDA device
+// is usable, compress() throws std::runtime_error.
+//
+// Contract notes:
+//   * level count / sizes: vkt_bcn_cuda_compress_plan == texture_block_compression.cpp:80-86,141-146
+//   * the image must be a crocore::Image_<uint8_t> with >= 3 components (the reference asserts, :68-69); 3-component
+//     images get alpha = 255 (get_block, :39-60)
+//   * delegate_fn is accepted and ignored: the GPU does the fan-out the reference delegates to a thread pool (:107-139)
+//   * duration is the whole call in milliseconds, never 0: the reference's own test asserts duration > 0 ms
+//     (tests/TestCompressionBC7.cpp:48) and a GPU call can finish in less than one
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include <vierkant/texture_block_compression.hpp>
+
+#include "vierkant_bcn_cuda.h"
+
+namespace vierkant::bcn
+{
+
+namespace
+{
+//! process-wide encoder context over every visible CUDA device (the role of the reference's init_helper_t, :29-37)
+struct cuda_context_t
+{
+    vkt_bcn_ctx *ctx = nullptr;
+    cuda_context_t()
+    {
+        if(vkt_bcn_cuda_create(&ctx, nullptr, 0) != VKT_BCN_OK)
+        {
+            throw std::runtime_error(std::string("vierkant::bcn (CUDA): ") + vkt_bcn_cuda_last_error(nullptr));
+        }
+    }
+    ~cuda_context_t() { vkt_bcn_cuda_destroy(ctx); }
+    cuda_context_t(const cuda_context_t &) = delete;
+    cuda_context_t &operator=(const cuda_context_t &) = delete;
+};
+}// namespace
+
+compress_result_t compress(const compress_info_t &compress_info)
+{
+    static cuda_context_t context;// thread-safe magic static, as in the reference (:66)
+
+    auto image = std::dynamic_pointer_cast<const crocore::Image_<uint8_t>>(compress_info.image);
+    if(!image || image->num_components() < 3)
+    {
+        throw std::invalid_argument("vierkant::bcn::compress: expected an 8-bit image with 3 or 4 components");
+    }
+    auto start_time = std::chrono::steady_clock::now();
+
+    vkt_bcn_plan plan = {};
+    if(vkt_bcn_cuda_compress_plan(image->width(), image->height(), compress_info.generate_mipmaps ? 1 : 0, &plan) != VKT_BCN_OK)
+    {
+        throw std::invalid_argument("vierkant::bcn::compress: empty image");
+    }
+    compress_result_t ret = {};
+    ret.mode = compress_info.mode;
+    ret.base_width = plan.base_width;
+    ret.base_height = plan.base_height;
+    ret.levels.resize(plan.num_levels);
+    void *level_ptrs[16] = {};
+    for(uint32_t l = 0; l < plan.num_levels; ++l)
+    {
+        ret.levels[l].resize(plan.level_num_blocks[l]);
+        level_ptrs[l] = ret.levels[l].data();
+    }
+    static_assert(sizeof(block_t) == 16, "block_t is the 16-byte BCn block");
+
+    // bc7enc_compress_block_params_init() defaults, as the reference uses them (:73-74); NULL selects them
+    const uint32_t mode = compress_info.mode == BC7 ? VKT_BCN_MODE_BC7 : VKT_BCN_MODE_BC5;
+    const int rc = vkt_bcn_cuda_compress(context.ctx, mode, static_cast<const uint8_t *>(image->data()), image->width(), image->height(),
+                                         image->num_components(), compress_info.generate_mipmaps ? 1 : 0, nullptr, level_ptrs);
+    if(rc != VKT_BCN_OK)
+    {
+        throw std::runtime_error(std::string("vierkant::bcn::compress (CUDA): ") + vkt_bcn_cuda_last_error(context.ctx));
+    }
+    auto elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start_time);
+    ret.duration = std::max(elapsed, std::chrono::milliseconds(1));
+    return ret;
+}
+
+}// namespace vierkant::bcn

@@ -57,6 +57,7 @@ EXPORTS = [
     "vkt_bcn_cuda_num_devices", "vkt_bcn_cuda_last_error", "vkt_bcn_cuda_encode_bc7", "vkt_bcn_cuda_encode_bc5",
     "vkt_bcn_cuda_encode_batch", "vkt_bcn_cuda_encode_bc7_device", "vkt_bcn_cuda_encode_bc5_device",
     "vkt_bcn_cuda_resize_u8", "vkt_bcn_cuda_compress_plan", "vkt_bcn_cuda_compress", "vkt_bcn_cuda_get_stats",
+    "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device",
 ]
 
 _lib = None
@@ -85,12 +86,14 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.vkt_bcn_cuda_encode_bc7.argtypes = [vp, vp, u32, u32, u32, u32, C.POINTER(Bc7Params), vp]
     L.vkt_bcn_cuda_encode_bc5.argtypes = [vp, vp, u32, u32, u32, u32, vp]
     L.vkt_bcn_cuda_encode_batch.argtypes = [vp, u32, C.POINTER(Image), u32, C.POINTER(Bc7Params)]
+    L.vkt_bcn_cuda_encode_batch_device.argtypes = [vp, C.c_int, u32, C.POINTER(Image), u32, C.POINTER(Bc7Params), vp]
     L.vkt_bcn_cuda_encode_bc7_device.argtypes = [vp, C.c_int, vp, u32, u32, u32, u32, C.POINTER(Bc7Params), vp, vp]
     L.vkt_bcn_cuda_encode_bc5_device.argtypes = [vp, C.c_int, vp, u32, u32, u32, u32, vp, vp]
     L.vkt_bcn_cuda_resize_u8.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32]
     L.vkt_bcn_cuda_compress_plan.argtypes = [u32, u32, C.c_int, C.POINTER(Plan)]
     L.vkt_bcn_cuda_compress.argtypes = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), C.POINTER(vp)]
     L.vkt_bcn_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.vkt_bcn_cuda_measure_issue_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     if path == _build.CUDA_SO:
         _lib = L
     return L
@@ -179,6 +182,12 @@ class BcnContext:
         self._check(self.lib.vkt_bcn_cuda_get_stats(self.handle, C.byref(s)))
         return {"kernel_launches": int(s.kernel_launches), "h2d_bytes": int(s.h2d_bytes), "d2h_bytes": int(s.d2h_bytes)}
 
+    def measure_issue_peak(self, slot: int = 0) -> float:
+        """Sustained integer issue rate of the device (lane-ops/s), measured by a short probe kernel."""
+        v = C.c_double()
+        self._check(self.lib.vkt_bcn_cuda_measure_issue_peak(self.handle, slot, C.byref(v)))
+        return float(v.value)
+
     # ---- host buffers -------------------------------------------------------------------------------------------
     def encode_bc7(self, img: np.ndarray, params: Bc7Params | None = None, out: np.ndarray | None = None) -> np.ndarray:
         """img: (H, W, C) uint8, H and W multiples of 4, C in {3, 4} -> (H/4 * W/4, 16) uint8 BC7 blocks."""
@@ -239,6 +248,17 @@ class BcnContext:
         pp = C.byref(params) if params is not None else None
         self._check(self.lib.vkt_bcn_cuda_encode_bc7_device(self.handle, slot, _ptr(d_pixels), width, height, comps,
                                                             row_stride, pp, _ptr(d_out), stream))
+
+    def make_device_batch(self, images: list, outs: list):
+        """(d_pixels, w, h, comps) tuples + device outputs -> a reusable vkt_bcn_image array for encode_batch_device."""
+        arr = (Image * len(images))()
+        for i, ((px, w, h, c), o) in enumerate(zip(images, outs)):
+            arr[i] = Image(_ptr(px), w, h, c, 0, _ptr(o))
+        return arr
+
+    def encode_batch_device(self, mode: int, batch, params: Bc7Params | None = None, slot: int = 0, stream: int | None = None) -> None:
+        pp = C.byref(params) if params is not None else None
+        self._check(self.lib.vkt_bcn_cuda_encode_batch_device(self.handle, slot, mode, batch, len(batch), pp, stream))
 
     def encode_bc5_device(self, d_pixels, width: int, height: int, comps: int, d_out, slot: int = 0,
                           stream: int | None = None, row_stride: int = 0) -> None:

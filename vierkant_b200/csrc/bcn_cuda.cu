@@ -72,36 +72,66 @@ constexpr int kBc7Threads = VKT_BC7_THREADS;
 // Alpha blocks carry a fourth channel through every stage: 2 CTAs/SM at <= 128 registers (no spills) is faster.
 constexpr int kBc7CtasPerSm = VKT_BC7_CTAS, kBc7CtasPerSmAlpha = VKT_BC7_CTAS_ALPHA;
 
-// Stage 0: split the level's blocks into an opaque and an alpha work list (the dispatch of bc7enc_compress_block,
+// Up to 16 images (the levels of a mip chain, the textures of a material, or row slices of them) are encoded by ONE
+// launch: the block index space of the launch is the concatenation of the images' block arrays.  A tail of tiny mip
+// levels otherwise costs one full block latency (~130 us) per level, serialised on the stream.
+constexpr uint32_t kBc7MaxImages = 16;
+struct Bc7Image
+{
+    const uint8_t *img;
+    uint4 *out;
+    uint32_t blocks_x, first_block;// first_block: position of the image's block 0 in the launch's index space
+    uint32_t comps, stride;
+    int vec16;
+};
+struct Bc7Batch
+{
+    Bc7Image im[kBc7MaxImages];
+    uint32_t num_images, total_blocks;
+};
+
+__device__ __forceinline__ uint32_t batch_find(const Bc7Batch &B, uint32_t g)
+{
+    uint32_t k = 0;
+#pragma unroll
+    for(uint32_t i = 1; i < kBc7MaxImages; ++i) { k += (i < B.num_images && g >= B.im[i].first_block) ? 1u : 0u; }
+    return k;
+}
+
+// Stage 0: split the launch's blocks into an opaque and an alpha work list (the dispatch of bc7enc_compress_block,
 // bc7enc.cpp:2422-2437), so that every warp of the encode kernels holds blocks of one kind.  counts[0] = #opaque,
-// counts[1] = #alpha.  List order is irrelevant to the output (block b always lands in out[b]); warp-aggregated
+// counts[1] = #alpha.  List order is irrelevant to the output (a block always lands in its own slot); warp-aggregated
 // atomics keep it nearly sorted, so the encode kernels' texel loads stay coalesced.
-__global__ void __launch_bounds__(256) bc7_classify_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks,
-                                                            uint32_t stride, int vec16, uint32_t *__restrict__ counts,
+__global__ void __launch_bounds__(256) bc7_classify_kernel(const __grid_constant__ Bc7Batch B, uint32_t *__restrict__ counts,
                                                             uint32_t *__restrict__ list_opaque, uint32_t *__restrict__ list_alpha)
 {
-    const uint32_t b = blockIdx.x * 256 + threadIdx.x;
-    const bool valid = b < num_blocks;
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = g < B.total_blocks;
     bool alpha = false;
     if(valid)
     {
-        const uint32_t bx = b % blocks_x, by = b / blocks_x;
+        const Bc7Image &I = B.im[batch_find(B, g)];
+        const uint32_t b = g - I.first_block;
+        const uint32_t bx = b % I.blocks_x, by = b / I.blocks_x;
         uint32_t and_all = 0xFFFFFFFFu;
-        if(vec16)
+        if(I.comps == 4)// 3-component images are opaque by construction (get_block injects alpha = 255)
         {
+            if(I.vec16)
+            {
 #pragma unroll
-            for(int y = 0; y < 4; ++y)
-            {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(img + size_t(by * 4 + y) * stride) + bx);
-                and_all &= v.x & v.y & v.z & v.w;
+                for(int y = 0; y < 4; ++y)
+                {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(I.img + size_t(by * 4 + y) * I.stride) + bx);
+                    and_all &= v.x & v.y & v.z & v.w;
+                }
             }
-        }
-        else
-        {
-            for(int y = 0; y < 4; ++y)
+            else
             {
-                const uint8_t *row = img + size_t(by * 4 + y) * stride + size_t(bx) * 16;
-                for(int x = 0; x < 4; ++x) { and_all &= uint32_t(row[4 * x + 3]) << 24; }
+                for(int y = 0; y < 4; ++y)
+                {
+                    const uint8_t *row = I.img + size_t(by * 4 + y) * I.stride + size_t(bx) * 16;
+                    for(int x = 0; x < 4; ++x) { and_all &= uint32_t(row[4 * x + 3]) << 24; }
+                }
             }
         }
         alpha = (and_all >> 24) != 255u;
@@ -118,21 +148,20 @@ __global__ void __launch_bounds__(256) bc7_classify_kernel(const uint8_t *__rest
     const uint32_t below = (1u << lane) - 1u;
     if(valid)
     {
-        if(alpha) { list_alpha[base_a + __popc(m_alpha & below)] = b; }
-        else { list_opaque[base_o + __popc(m_opaque & below)] = b; }
+        if(alpha) { list_alpha[base_a + __popc(m_alpha & below)] = g; }
+        else { list_opaque[base_o + __popc(m_opaque & below)] = g; }
     }
 }
 
-// One lane == one block of the work list (list == nullptr: every block of the level, in order).
+// One lane == one block of the work list (list == nullptr: every block of the launch, in order).
 template<bool PERC, bool KEY28, bool ALPHA, int NT>
 __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm)
-        bc7_encode_kernel(const uint8_t *__restrict__ img, uint32_t blocks_x, uint32_t num_blocks, uint32_t comps, uint32_t stride, int vec16,
-                          const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables, const uint32_t *__restrict__ list,
-                          const uint32_t *__restrict__ count, uint4 *__restrict__ out)
+        bc7_encode_kernel(const __grid_constant__ Bc7Batch B, const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables,
+                          const uint32_t *__restrict__ list, const uint32_t *__restrict__ count)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const uint32_t n = count ? __ldg(count) : num_blocks;
-    if(blockIdx.x * NT >= n) { return; }// the grid is sized for the whole level; lists are usually shorter
+    const uint32_t n = count ? __ldg(count) : B.total_blocks;
+    if(blockIdx.x * NT >= n) { return; }// the grid is sized for the whole launch; lists are usually shorter
     Bc7Tables &s_tables = *reinterpret_cast<Bc7Tables *>(s_raw);
     Texel *s_lane = reinterpret_cast<Texel *>(s_raw + sizeof(Bc7Tables));// one 16-record column per lane (see Lane<>)
     {
@@ -142,13 +171,15 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm
     }
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
     const uint32_t ii = min(i, n - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
-    const uint32_t b = list ? __ldg(list + ii) : ii;
+    const uint32_t g = list ? __ldg(list + ii) : ii;
+    const Bc7Image &I = B.im[batch_find(B, g)];
+    const uint32_t b = g - I.first_block;
     Lane<NT> lane{s_lane + threadIdx.x};
-    load_block_texels<NT>(img, comps, stride, vec16 != 0, b % blocks_x, b / blocks_x, lane.p);
+    load_block_texels<NT>(I.img, I.comps, I.stride, I.vec16 != 0, b % I.blocks_x, b / I.blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
     encode_block<PERC, KEY28, ALPHA, NT>(s_tables, P, lane, blk);
-    if(i < n) { out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
+    if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Tables) + size_t(kBc7Threads) * 16 * sizeof(Texel);
@@ -172,6 +203,36 @@ static cudaError_t bc7_kernel_attributes()
     return e;
 }
 
+// ------------------------------------------------------------------------------------------------ issue-rate probe
+// Measurement support: the ALU roofline's denominator.  Eight independent chains per thread, half the
+// instructions on the FMA pipe (IMAD), half on the ALU pipe (LOP3 / IADD3) -- the mix at which an SM sub-partition can
+// issue one warp instruction per clock.  32 lane-operations per warp instruction.
+__global__ void __launch_bounds__(256) alu_probe_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8], b[8];
+#pragma unroll
+    for(int k = 0; k < 8; ++k) { a[k] = seed + threadIdx.x * 8u + k, b[k] = seed * 3u + k; }
+#pragma unroll 1
+    for(int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for(int r = 0; r < 4; ++r)
+        {
+#pragma unroll
+            for(int k = 0; k < 8; ++k)
+            {
+                a[k] = a[k] * 0x9E3779B1u + b[k];// IMAD
+                b[k] = b[k] ^ a[k];// LOP3
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for(int k = 0; k < 8; ++k) { acc += a[k] ^ b[k]; }
+    if(acc == 0x12345u) { out[blockIdx.x * 256 + threadIdx.x] = acc; }
+}
+constexpr int kProbeOpsPerIter = 4 * 8 * 2;// per thread and iteration: 4 rounds x 8 chains x (IMAD + LOP3)
+
 // ------------------------------------------------------------------------------------------------ context
 }// namespace vkt
 struct vkt_axis_cache;// resize_core.cuh
@@ -181,7 +242,7 @@ struct DeviceSlot
 {
     vkt_axis_cache *axis_cache = nullptr;
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;// stream2: second lane of the host-batch pipeline
     Bc7Tables *d_tables = nullptr;
     void *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
     size_t in_cap = 0, out_cap = 0, tmp_cap = 0;
@@ -260,9 +321,18 @@ static int check_image(vkt_bcn_ctx *ctx, const void *px, uint32_t w, uint32_t h,
     return VKT_BCN_OK;
 }
 
-// launch the BC7 kernel on device-resident data (current device must be the slot's)
-static int launch_bc7(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_t w, uint32_t h, uint32_t comps, uint32_t stride,
-                      const vkt_bc7_params *params, void *d_out, cudaStream_t stream)
+// One device-resident image (or row slice) of a launch.
+struct DevImage
+{
+    const void *d_px;
+    uint32_t w, h, comps, stride;
+    void *d_out;
+};
+
+// launch the BC7 kernels on device-resident data (current device must be the slot's): all images in as few launches as
+// possible (kBc7MaxImages per launch)
+static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *images, uint32_t num_images, const vkt_bc7_params *params,
+                            cudaStream_t stream)
 {
     vkt_bc7_params def;
     if(!params)
@@ -277,57 +347,78 @@ static int launch_bc7(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_
         return fail(ctx, rc, "unsupported bc7 parameters (force_selectors / quant_mode6_endpoints / low_frequency_partition_weight != 1)");
     }
     if(rc) { return fail(ctx, rc, "invalid bc7 parameters (mode_mask must enable mode 6 or 1 and one of 5/6/7; uber_level <= 4)"); }
-    const uint32_t bx = w / 4, nblocks = bx * (h / 4);
-    const int vec16 = (comps == 4) && ((stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d_px) & 15u) == 0);
-    const uint32_t grid = (nblocks + kBc7Threads - 1) / kBc7Threads;
-    const uint8_t *px = static_cast<const uint8_t *>(d_px);
-    uint4 *outp = static_cast<uint4 *>(d_out);
-    auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
-        auto go = [&](auto kernel) {
-            kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(px, bx, nblocks, comps, stride, vec16, kp, s->d_tables, list, cnt, outp);
-        };
-        const int sel = (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
-        switch(sel)
+    for(uint32_t first = 0; first < num_images; first += kBc7MaxImages)
+    {
+        Bc7Batch B = {};
+        B.num_images = std::min<uint32_t>(kBc7MaxImages, num_images - first);
+        uint64_t total = 0;
+        bool any4 = false;
+        for(uint32_t k = 0; k < B.num_images; ++k)
         {
-            case 7: go(bc7_encode_kernel<true, true, true, kBc7Threads>); break;
-            case 6: go(bc7_encode_kernel<true, true, false, kBc7Threads>); break;
-            case 5: go(bc7_encode_kernel<true, false, true, kBc7Threads>); break;
-            case 4: go(bc7_encode_kernel<true, false, false, kBc7Threads>); break;
-            case 3: go(bc7_encode_kernel<false, true, true, kBc7Threads>); break;
-            case 2: go(bc7_encode_kernel<false, true, false, kBc7Threads>); break;
-            case 1: go(bc7_encode_kernel<false, false, true, kBc7Threads>); break;
-            default: go(bc7_encode_kernel<false, false, false, kBc7Threads>); break;
+            const DevImage &d = images[first + k];
+            Bc7Image &I = B.im[k];
+            I.img = static_cast<const uint8_t *>(d.d_px), I.out = static_cast<uint4 *>(d.d_out);
+            I.blocks_x = d.w / 4, I.first_block = uint32_t(total), I.comps = d.comps, I.stride = d.stride;
+            I.vec16 = (d.comps == 4) && ((d.stride & 15u) == 0) && ((reinterpret_cast<uintptr_t>(d.d_px) & 15u) == 0);
+            total += uint64_t(d.w / 4) * (d.h / 4);
+            any4 = any4 || d.comps == 4;
         }
-    };
-    if(kp.force_alpha)
-    {
-        encode(true, nullptr, nullptr);
-        count(ctx, 1, 0, 0);
+        if(total == 0) { continue; }
+        if(total > 0xFFFFFFF0ull) { return fail(ctx, VKT_BCN_ERR_INVALID, "more than 2^32 blocks in one launch"); }
+        B.total_blocks = uint32_t(total);
+        const uint32_t grid = (B.total_blocks + kBc7Threads - 1) / kBc7Threads;
+        auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
+            auto go = [&](auto kernel) { kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(B, kp, s->d_tables, list, cnt); };
+            const int sel = (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            switch(sel)
+            {
+                case 7: go(bc7_encode_kernel<true, true, true, kBc7Threads>); break;
+                case 6: go(bc7_encode_kernel<true, true, false, kBc7Threads>); break;
+                case 5: go(bc7_encode_kernel<true, false, true, kBc7Threads>); break;
+                case 4: go(bc7_encode_kernel<true, false, false, kBc7Threads>); break;
+                case 3: go(bc7_encode_kernel<false, true, true, kBc7Threads>); break;
+                case 2: go(bc7_encode_kernel<false, true, false, kBc7Threads>); break;
+                case 1: go(bc7_encode_kernel<false, false, true, kBc7Threads>); break;
+                default: go(bc7_encode_kernel<false, false, false, kBc7Threads>); break;
+            }
+        };
+        if(kp.force_alpha)
+        {
+            encode(true, nullptr, nullptr);
+            count(ctx, 1, 0, 0);
+        }
+        else if(!any4)
+        {
+            encode(false, nullptr, nullptr);// get_block injects alpha = 255: every block is opaque
+            count(ctx, 1, 0, 0);
+        }
+        else
+        {
+            // stream-ordered scratch: [counts: 2 x u32, padded to 256 B][opaque list][alpha list]
+            uint8_t *scratch = nullptr;
+            const size_t list_bytes = align_up(size_t(B.total_blocks) * sizeof(uint32_t), 256);
+            VKT_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), 256 + 2 * list_bytes, stream));
+            uint32_t *counts = reinterpret_cast<uint32_t *>(scratch);
+            uint32_t *list_o = reinterpret_cast<uint32_t *>(scratch + 256), *list_a = reinterpret_cast<uint32_t *>(scratch + 256 + list_bytes);
+            VKT_CUDA(ctx, cudaMemsetAsync(counts, 0, 8, stream));
+            bc7_classify_kernel<<<(B.total_blocks + 255) / 256, 256, 0, stream>>>(B, counts, list_o, list_a);
+            encode(false, list_o, counts);
+            encode(true, list_a, counts + 1);
+            const cudaError_t e = cudaGetLastError();
+            VKT_CUDA(ctx, cudaFreeAsync(scratch, stream));
+            VKT_CUDA(ctx, e);
+            count(ctx, 3, 0, 0);
+        }
+        VKT_CUDA(ctx, cudaGetLastError());
     }
-    else if(comps == 3)
-    {
-        encode(false, nullptr, nullptr);// get_block injects alpha = 255: every block is opaque
-        count(ctx, 1, 0, 0);
-    }
-    else
-    {
-        // stream-ordered scratch: [counts: 2 x u32, padded to 256 B][opaque list][alpha list]
-        uint8_t *scratch = nullptr;
-        const size_t list_bytes = align_up(size_t(nblocks) * sizeof(uint32_t), 256);
-        VKT_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), 256 + 2 * list_bytes, stream));
-        uint32_t *counts = reinterpret_cast<uint32_t *>(scratch);
-        uint32_t *list_o = reinterpret_cast<uint32_t *>(scratch + 256), *list_a = reinterpret_cast<uint32_t *>(scratch + 256 + list_bytes);
-        VKT_CUDA(ctx, cudaMemsetAsync(counts, 0, 8, stream));
-        bc7_classify_kernel<<<(nblocks + 255) / 256, 256, 0, stream>>>(px, bx, nblocks, stride, vec16, counts, list_o, list_a);
-        encode(false, list_o, counts);
-        encode(true, list_a, counts + 1);
-        const cudaError_t e = cudaGetLastError();
-        VKT_CUDA(ctx, cudaFreeAsync(scratch, stream));
-        VKT_CUDA(ctx, e);
-        count(ctx, 3, 0, 0);
-    }
-    VKT_CUDA(ctx, cudaGetLastError());
     return VKT_BCN_OK;
+}
+
+static int launch_bc7(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_t w, uint32_t h, uint32_t comps, uint32_t stride,
+                      const vkt_bc7_params *params, void *d_out, cudaStream_t stream)
+{
+    const DevImage d{d_px, w, h, comps, stride, d_out};
+    return launch_bc7_batch(ctx, s, &d, 1, params, stream);
 }
 
 static int launch_bc5(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_t w, uint32_t h, uint32_t comps, uint32_t stride,
@@ -338,35 +429,6 @@ static int launch_bc5(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_
     bc5_encode_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t *>(d_px), bx, nblocks, comps, stride, static_cast<uint4 *>(d_out));
     VKT_CUDA(ctx, cudaGetLastError());
     count(ctx, 1, 0, 0);
-    return VKT_BCN_OK;
-}
-
-// Encode block rows [row0, row1) of one host image on one slot: async H2D, kernel, async D2H on the slot's stream.
-// The caller synchronises the stream.  Pinned host memory makes both copies truly asynchronous.
-static int encode_rows_async(vkt_bcn_ctx *ctx, DeviceSlot *s, uint32_t mode, const vkt_bcn_image &img, uint32_t row0, uint32_t row1,
-                             const vkt_bc7_params *params, size_t in_off, size_t out_off)
-{
-    const uint32_t stride = img.row_stride_bytes ? img.row_stride_bytes : img.width * img.comps;
-    const uint32_t rows = row1 - row0;
-    if(rows == 0) { return VKT_BCN_OK; }
-    const size_t row_bytes = size_t(img.width) * img.comps;
-    const size_t in_bytes = size_t(rows) * 4 * row_bytes;
-    const size_t out_bytes = size_t(rows) * (img.width / 4) * 16;
-    uint8_t *d_in = static_cast<uint8_t *>(s->d_in) + in_off;
-    uint8_t *d_out = static_cast<uint8_t *>(s->d_out) + out_off;
-    const uint8_t *h_in = img.pixels + size_t(row0) * 4 * stride;
-    // device copy is tightly packed
-    VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, h_in, stride, row_bytes, size_t(rows) * 4, cudaMemcpyHostToDevice, s->stream));
-    int rc;
-    if(mode == VKT_BCN_MODE_BC7)
-    {
-        rc = launch_bc7(ctx, s, d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), params, d_out, s->stream);
-    }
-    else { rc = launch_bc5(ctx, s, d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), d_out, s->stream); }
-    if(rc) { return rc; }
-    VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(img.out_blocks) + size_t(row0) * (img.width / 4) * 16, d_out, out_bytes,
-                                  cudaMemcpyDeviceToHost, s->stream));
-    count(ctx, 0, in_bytes, out_bytes);
     return VKT_BCN_OK;
 }
 
@@ -418,6 +480,7 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         ctx->slots.push_back(s);
         cudaError_t e = cudaSetDevice(dev);
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
         if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
         if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
@@ -452,6 +515,11 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
             {
                 cudaStreamSynchronize(s->stream);
                 cudaStreamDestroy(s->stream);
+            }
+            if(s->stream2)
+            {
+                cudaStreamSynchronize(s->stream2);
+                cudaStreamDestroy(s->stream2);
             }
             cudaFree(s->d_tables);
             cudaFree(s->d_in);
@@ -504,8 +572,9 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
     }
     const uint32_t G = uint32_t(ctx->slots.size());
     // Partition: every image's block rows are split evenly over the G devices; images with fewer
-    // block rows than devices go to one device, rotating.  Per slot, all its pieces are queued back to back on its
-    // stream (H2D -> kernel -> D2H per piece), then every stream is synchronised once.
+    // block rows than devices go to one device, rotating.  Per device the pieces are cut into groups (<= 16 images,
+    // ~1 M blocks): a group is H2D copies -> ONE encode launch over all its pieces -> D2H copies, and consecutive
+    // groups alternate between the slot's two streams so that the copies of one overlap the kernels of the other.
     struct Piece
     {
         uint32_t img, row0, row1;
@@ -545,18 +614,55 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, in_need[g]))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_need[g]))) { break; }
     }
-    // queue piece by piece, round-robin over devices so that all PCIe links start early
-    size_t max_pieces = 0;
-    for(auto &p: plan) { max_pieces = std::max(max_pieces, p.size()); }
-    for(size_t k = 0; k < max_pieces && !rc; ++k)
+    // queue group by group, round-robin over devices so that all PCIe links start early
+    constexpr uint64_t kGroupBlocks = 1u << 20;
+    std::vector<size_t> next(G, 0), group_no(G, 0);
+    bool more = !rc;
+    while(more && !rc)
     {
+        more = false;
         for(uint32_t g = 0; g < G && !rc; ++g)
         {
-            if(k >= plan[g].size()) { continue; }
+            if(next[g] >= plan[g].size()) { continue; }
             DeviceSlot *s = ctx->slots[g];
-            const Piece &p = plan[g][k];
             VKT_CUDA(ctx, cudaSetDevice(s->device));
-            rc = encode_rows_async(ctx, s, mode, images[p.img], p.row0, p.row1, params, p.in_off, p.out_off);
+            cudaStream_t st = (group_no[g]++ & 1) ? s->stream2 : s->stream;
+            const size_t first = next[g];
+            uint64_t blocks = 0;
+            std::vector<DevImage> dev;
+            while(next[g] < plan[g].size() && dev.size() < kBc7MaxImages && (dev.empty() || blocks < kGroupBlocks))
+            {
+                const Piece &p = plan[g][next[g]++];
+                const vkt_bcn_image &img = images[p.img];
+                const uint32_t stride = img.row_stride_bytes ? img.row_stride_bytes : img.width * img.comps;
+                const uint32_t rows = p.row1 - p.row0;
+                const size_t row_bytes = size_t(img.width) * img.comps;
+                uint8_t *d_in = static_cast<uint8_t *>(s->d_in) + p.in_off;
+                // the device copy is tightly packed
+                VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, img.pixels + size_t(p.row0) * 4 * stride, stride, row_bytes, size_t(rows) * 4,
+                                                cudaMemcpyHostToDevice, st));
+                dev.push_back({d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), static_cast<uint8_t *>(s->d_out) + p.out_off});
+                blocks += uint64_t(rows) * (img.width / 4);
+                count(ctx, 0, size_t(rows) * 4 * row_bytes, 0);
+            }
+            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, st); }
+            else
+            {
+                for(const DevImage &d: dev)
+                {
+                    if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, st))) { break; }
+                }
+            }
+            for(size_t k = first; k < next[g] && !rc; ++k)
+            {
+                const Piece &p = plan[g][k];
+                const vkt_bcn_image &img = images[p.img];
+                const size_t row_blk = size_t(img.width / 4) * 16, bytes = size_t(p.row1 - p.row0) * row_blk;
+                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(img.out_blocks) + size_t(p.row0) * row_blk,
+                                              static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDeviceToHost, st));
+                count(ctx, 0, 0, bytes);
+            }
+            more = more || next[g] < plan[g].size();
         }
     }
     for(uint32_t g = 0; g < G; ++g)
@@ -564,7 +670,9 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         DeviceSlot *s = ctx->slots[g];
         if(plan[g].empty()) { continue; }
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
-        const cudaError_t e = cudaStreamSynchronize(s->stream);
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        const cudaError_t e2 = cudaStreamSynchronize(s->stream2);
+        if(e == cudaSuccess) { e = e2; }
         if(e != cudaSuccess && !rc) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
     }
     return rc;
@@ -601,6 +709,39 @@ static int device_entry(vkt_bcn_ctx *ctx, int slot, uint32_t mode, const void *d
     return VKT_BCN_OK;
 }
 
+int vkt_bcn_cuda_encode_batch_device(vkt_bcn_ctx *ctx, int slot, uint32_t mode, const vkt_bcn_image *images, uint32_t num_images,
+                                     const vkt_bc7_params *params, void *cuda_stream)
+{
+    if(!ctx) { return VKT_BCN_ERR_INVALID; }
+    if(mode != VKT_BCN_MODE_BC7 && mode != VKT_BCN_MODE_BC5) { return fail(ctx, VKT_BCN_ERR_INVALID, "unknown mode %u", mode); }
+    if(num_images && !images) { return fail(ctx, VKT_BCN_ERR_INVALID, "null image array"); }
+    if(slot < 0 || slot >= int(ctx->slots.size())) { return fail(ctx, VKT_BCN_ERR_INVALID, "slot %d out of range", slot); }
+    std::vector<DevImage> dev;
+    for(uint32_t i = 0; i < num_images; ++i)
+    {
+        uint32_t stride = images[i].row_stride_bytes;
+        const int rc = check_image(ctx, images[i].pixels, images[i].width, images[i].height, images[i].comps, &stride, images[i].out_blocks);
+        if(rc) { return rc; }
+        dev.push_back({images[i].pixels, images[i].width, images[i].height, images[i].comps, stride, images[i].out_blocks});
+    }
+    DeviceSlot *s = ctx->slots[size_t(slot)];
+    std::lock_guard<std::mutex> g(s->mtx);
+    VKT_CUDA(ctx, cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
+    int rc = VKT_BCN_OK;
+    if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, st); }
+    else
+    {
+        for(const DevImage &d: dev)
+        {
+            if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, st))) { break; }
+        }
+    }
+    if(rc) { return rc; }
+    if(!cuda_stream) { VKT_CUDA(ctx, cudaStreamSynchronize(st)); }
+    return VKT_BCN_OK;
+}
+
 int vkt_bcn_cuda_encode_bc7_device(vkt_bcn_ctx *ctx, int slot, const void *d_pixels, uint32_t width, uint32_t height, uint32_t comps,
                                    uint32_t row_stride_bytes, const vkt_bc7_params *params, void *d_out_blocks, void *cuda_stream)
 {
@@ -632,6 +773,38 @@ int vkt_bcn_cuda_compress_plan(uint32_t width, uint32_t height, int generate_mip
         plan->level_num_blocks[l] = uint64_t(w / 4) * (h / 4);
         w = round4(std::max<uint32_t>(w / 2, 1)), h = round4(std::max<uint32_t>(h / 2, 1));
     }
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_measure_issue_peak(vkt_bcn_ctx *ctx, int slot, double *lane_ops_per_second)
+{
+    if(!ctx || !lane_ops_per_second) { return VKT_BCN_ERR_INVALID; }
+    if(slot < 0 || slot >= int(ctx->slots.size())) { return fail(ctx, VKT_BCN_ERR_INVALID, "slot %d out of range", slot); }
+    DeviceSlot *s = ctx->slots[size_t(slot)];
+    std::lock_guard<std::mutex> g(s->mtx);
+    VKT_CUDA(ctx, cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    VKT_CUDA(ctx, cudaGetDeviceProperties(&prop, s->device));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    int rc = ensure(ctx, &s->d_tmp, &s->tmp_cap, size_t(grid) * 256 * sizeof(uint32_t));
+    if(rc) { return rc; }
+    cudaEvent_t e0, e1;
+    VKT_CUDA(ctx, cudaEventCreate(&e0));
+    VKT_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 0.0f;
+    for(int rep = 0; rep < 4; ++rep)
+    {
+        VKT_CUDA(ctx, cudaEventRecord(e0, s->stream));
+        alu_probe_kernel<<<grid, 256, 0, s->stream>>>(static_cast<uint32_t *>(s->d_tmp), iters, 17u + rep);
+        VKT_CUDA(ctx, cudaEventRecord(e1, s->stream));
+        VKT_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        VKT_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if(rep > 0 && (best == 0.0f || ms < best)) { best = ms; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lane_ops_per_second = double(grid) * 256.0 * iters * kProbeOpsPerIter / (double(best) * 1e-3);
     return VKT_BCN_OK;
 }
 

@@ -276,6 +276,12 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         count(ctx, 0, src_bytes, 0);
         const uint8_t *prev = d_src;
         uint32_t pw = width, ph = height;
+        struct Slice
+        {
+            uint32_t level, r0, r1;
+        };
+        std::vector<Slice> slices;
+        std::vector<DevImage> dev;
         for(uint32_t l = 0; l < plan.num_levels && !rc; ++l)
         {
             const uint32_t w = plan.level_width[l], h = plan.level_height[l];
@@ -289,13 +295,26 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             else { r0 = uint32_t(uint64_t(rows) * g / G), r1 = uint32_t(uint64_t(rows) * (g + 1) / G); }
             if(r0 >= r1) { continue; }
             const size_t row_px = size_t(w) * comps * 4, row_blk = size_t(w / 4) * 16;
-            uint8_t *d_blk = static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk;
-            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7(ctx, s, cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, params, d_blk, s->stream); }
-            else { rc = launch_bc5(ctx, s, cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, d_blk, s->stream); }
-            if(rc) { break; }
-            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[l]) + size_t(r0) * row_blk, d_blk, size_t(r1 - r0) * row_blk,
+            slices.push_back({l, r0, r1});
+            dev.push_back({cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk});
+        }
+        if(rc) { break; }
+        // every level of the chain in one set of launches, then the gather
+        if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
+        else
+        {
+            for(const DevImage &d: dev)
+            {
+                if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream))) { break; }
+            }
+        }
+        for(size_t k = 0; k < slices.size() && !rc; ++k)
+        {
+            const Slice &sl = slices[k];
+            const size_t row_blk = size_t(plan.level_width[sl.level] / 4) * 16, bytes = size_t(sl.r1 - sl.r0) * row_blk;
+            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[sl.level]) + size_t(sl.r0) * row_blk, dev[k].d_out, bytes,
                                           cudaMemcpyDeviceToHost, s->stream));
-            count(ctx, 0, 0, size_t(r1 - r0) * row_blk);
+            count(ctx, 0, 0, bytes);
         }
     }
     for(uint32_t g = 0; g < G; ++g)
