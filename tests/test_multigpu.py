@@ -1,0 +1,44 @@
+"""One context over several B200s (run with gpurun --gpus N): block rows / levels are split over the devices and gathered
+with async copies; the result must be byte-identical to the single-device one.  Skipped on single-GPU boxes."""
+import numpy as np
+import pytest
+
+from vierkant_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def multi_ctx(cuda_lib):
+    n = capi.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    c = capi.BcnContext(list(range(n)))
+    yield c
+    c.close()
+
+
+def test_encode_rows_split_over_devices(ctx, multi_ctx):
+    img = synth.make_texture(1024, 512, 1, seed=3)
+    assert multi_ctx.num_devices >= 2
+    assert np.array_equal(multi_ctx.encode_bc7(img), ctx.encode_bc7(img))
+    assert np.array_equal(multi_ctx.encode_bc5(img), ctx.encode_bc5(img))
+
+
+def test_compress_chain_split_over_devices(ctx, multi_ctx):
+    img = synth.make_texture(1000, 520, 1, seed=4)
+    _, a = multi_ctx.compress(img, capi.MODE_BC7, True)
+    _, b = ctx.compress(img, capi.MODE_BC7, True)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_batch_of_textures_over_devices(ctx, multi_ctx):
+    imgs = [synth.make_texture(256 >> (i % 3), 128, i & 1, seed=10 + i) for i in range(9)]
+    outs_a = [np.empty(((i.shape[0] // 4) * (i.shape[1] // 4), 16), dtype=np.uint8) for i in imgs]
+    outs_b = [np.empty_like(o) for o in outs_a]
+    multi_ctx.encode_batch(capi.MODE_BC7, imgs, outs_a)
+    ctx.encode_batch(capi.MODE_BC7, imgs, outs_b)
+    for x, y in zip(outs_a, outs_b):
+        assert np.array_equal(x, y)
