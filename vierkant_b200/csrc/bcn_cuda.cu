@@ -242,7 +242,8 @@ struct DeviceSlot
 {
     vkt_axis_cache *axis_cache = nullptr;
     int device = -1;
-    cudaStream_t stream = nullptr, stream2 = nullptr;// stream2: second lane of the host-batch pipeline
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;// 2: uploads / second batch lane, 3: downloads
+    cudaStream_t stream4 = nullptr, stream5 = nullptr;                  // encode ping-pong of the pipelined chain
     Bc7Tables *d_tables = nullptr;
     void *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
     size_t in_cap = 0, out_cap = 0, tmp_cap = 0;
@@ -481,6 +482,9 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         cudaError_t e = cudaSetDevice(dev);
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream5, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
         if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
         if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
@@ -515,6 +519,14 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
             {
                 cudaStreamSynchronize(s->stream);
                 cudaStreamDestroy(s->stream);
+            }
+            for(cudaStream_t st: {s->stream3, s->stream4, s->stream5})
+            {
+                if(st)
+                {
+                    cudaStreamSynchronize(st);
+                    cudaStreamDestroy(st);
+                }
             }
             if(s->stream2)
             {

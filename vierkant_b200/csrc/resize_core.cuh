@@ -166,22 +166,25 @@ static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, const Devi
 constexpr size_t kResizeBandBytes = size_t(256) << 20;// fp32 band buffer budget per slot
 
 // d_src (w x h x comps, tightly packed, device) -> d_dst (ow x oh x comps).  Work is queued on `stream`.
+// out_y0 / out_y1 restrict the call to a range of output rows (out_y1 == 0: all rows).
 static int resize_device(vkt_bcn_ctx *ctx, DeviceSlot *s, const uint8_t *d_src, uint32_t w, uint32_t h, uint32_t comps, uint8_t *d_dst,
-                         uint32_t ow, uint32_t oh, cudaStream_t stream)
+                         uint32_t ow, uint32_t oh, cudaStream_t stream, uint32_t out_y0 = 0, uint32_t out_y1 = 0)
 {
+    if(out_y1 == 0) { out_y1 = oh; }
     const DeviceAxis *ax = nullptr, *ay = nullptr;
     int rc = get_axis(ctx, s, int(w), int(ow), &ax);
     if(rc) { return rc; }
     if((rc = get_axis(ctx, s, int(h), int(oh), &ay))) { return rc; }
     const size_t row_bytes = size_t(ow) * comps * sizeof(float);
     // output-row bands whose input-row span fits the budget (at least one output row per band)
-    uint32_t y0 = 0;
-    while(y0 < oh)
+    uint32_t y0 = out_y0;
+    while(y0 < out_y1)
     {
         const int r_lo = ay->first_in[y0];
         uint32_t y1 = y0 + 1;
         int r_hi = ay->last_in[y0];
-        while(y1 < oh && size_t(std::max(r_hi, ay->last_in[y1]) - r_lo + 1) * row_bytes <= kResizeBandBytes)
+        while(y1 < out_y1 && (y1 - y0) < 32768u && (std::max(r_hi, ay->last_in[y1]) - r_lo + 1) <= 32768 &&
+              size_t(std::max(r_hi, ay->last_in[y1]) - r_lo + 1) * row_bytes <= kResizeBandBytes)
         {
             r_hi = std::max(r_hi, ay->last_in[y1]);
             ++y1;
@@ -265,6 +268,18 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     std::vector<std::unique_lock<std::mutex>> locks;
     for(uint32_t g = 0; g < G; ++g) { locks.emplace_back(ctx->slots[g]->mtx); }
     int rc = VKT_BCN_OK;
+    // Level 0 is pipelined in K row bands over several streams per device -- upload (stream2) -> resize (stream) -> encode
+    // (stream4 / stream5 alternating, so the tail wave of one band overlaps the head of the next) -> download (stream3)
+    // -- so that PCIe traffic hides behind the encode kernels; the remaining levels (a quarter of the work) follow as
+    // one launch set.
+    const uint32_t rows0 = plan.level_height[0] / 4;
+    const uint32_t K = plan.level_num_blocks[0] >= (1u << 18) ? 8u : (plan.level_num_blocks[0] >= (1u << 14) ? 2u : 1u);
+    std::vector<cudaEvent_t> events;
+    auto new_event = [&](cudaEvent_t *e) -> cudaError_t {
+        const cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if(r == cudaSuccess) { events.push_back(*e); }
+        return r;
+    };
     for(uint32_t g = 0; g < G && !rc; ++g)
     {
         DeviceSlot *s = ctx->slots[g];
@@ -272,17 +287,89 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_total))) { break; }
         uint8_t *d_src = static_cast<uint8_t *>(s->d_in), *d_lvl = d_src + align_up(src_bytes, 256);
-        VKT_CUDA(ctx, cudaMemcpyAsync(d_src, pixels, src_bytes, cudaMemcpyHostToDevice, s->stream));
-        count(ctx, 0, src_bytes, 0);
-        const uint8_t *prev = d_src;
-        uint32_t pw = width, ph = height;
+        const DeviceAxis *ay0 = nullptr;
+        if((rc = get_axis(ctx, s, int(height), int(plan.level_height[0]), &ay0))) { break; }
+        // this device's block rows of level 0
+        uint32_t own0, own1;
+        if(rows0 < G * 4) { own0 = (0 % G == g) ? 0 : rows0, own1 = rows0; }
+        else { own0 = uint32_t(uint64_t(rows0) * g / G), own1 = uint32_t(uint64_t(rows0) * (g + 1) / G); }
+        // source-row bands of the upload
+        const size_t src_row = size_t(width) * comps;
+        std::vector<uint32_t> up_end(K);
+        std::vector<cudaEvent_t> up_done(K);
+        for(uint32_t k = 0; k < K; ++k) { up_end[k] = uint32_t(uint64_t(height) * (k + 1) / K); }
+        uint32_t uploaded = 0;// number of upload bands queued
+        auto upload = [&](uint32_t k) -> int {
+            const uint32_t y0 = k ? up_end[k - 1] : 0, y1 = up_end[k];
+            if(y1 > y0)
+            {
+                VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(y0) * src_row, pixels + size_t(y0) * src_row, size_t(y1 - y0) * src_row,
+                                              cudaMemcpyHostToDevice, s->stream2));
+                count(ctx, 0, size_t(y1 - y0) * src_row, 0);
+            }
+            VKT_CUDA(ctx, new_event(&up_done[k]));
+            VKT_CUDA(ctx, cudaEventRecord(up_done[k], s->stream2));
+            return VKT_BCN_OK;
+        };
+        const uint32_t w0 = plan.level_width[0], h0 = plan.level_height[0];
+        uint8_t *lvl0 = d_lvl + lvl_off[0];
+        const size_t row_px0 = size_t(w0) * comps * 4, row_blk0 = size_t(w0 / 4) * 16;
+        for(uint32_t k = 0; k < K && !rc; ++k)
+        {
+            const uint32_t b0 = uint32_t(uint64_t(rows0) * k / K), b1 = uint32_t(uint64_t(rows0) * (k + 1) / K);// block rows of the band
+            if(b1 <= b0) { continue; }
+            // uploads needed by this band's resize: every source row up to the last tap of its last output row
+            const uint32_t need_row = uint32_t(ay0->last_in[size_t(b1) * 4 - 1]);
+            while(uploaded < K && (uploaded == 0 || up_end[uploaded - 1] <= need_row))
+            {
+                if((rc = upload(uploaded))) { break; }
+                ++uploaded;
+            }
+            if(rc) { break; }
+            if(k + 1 < K && uploaded < K)// keep the link busy: queue the next upload before this band's kernels
+            {
+                if((rc = upload(uploaded))) { break; }
+                ++uploaded;
+            }
+            uint32_t need_band = 0;
+            while(need_band + 1 < K && up_end[need_band] <= need_row) { ++need_band; }
+            VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, up_done[need_band], 0));
+            if((rc = resize_device(ctx, s, d_src, width, height, comps, lvl0, w0, h0, s->stream, b0 * 4, b1 * 4))) { break; }
+            const uint32_t e0 = std::max(b0, own0), e1 = std::min(b1, own1);
+            if(e0 >= e1) { continue; }
+            cudaEvent_t resized;
+            VKT_CUDA(ctx, new_event(&resized));
+            VKT_CUDA(ctx, cudaEventRecord(resized, s->stream));
+            cudaStream_t enc = (k & 1u) ? s->stream5 : s->stream4;
+            VKT_CUDA(ctx, cudaStreamWaitEvent(enc, resized, 0));
+            uint8_t *d_blk = static_cast<uint8_t *>(s->d_out) + out_off[0] + size_t(e0) * row_blk0;
+            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7(ctx, s, lvl0 + size_t(e0) * row_px0, w0, (e1 - e0) * 4, comps, w0 * comps, params, d_blk, enc); }
+            else { rc = launch_bc5(ctx, s, lvl0 + size_t(e0) * row_px0, w0, (e1 - e0) * 4, comps, w0 * comps, d_blk, enc); }
+            if(rc) { break; }
+            cudaEvent_t enc_done;
+            VKT_CUDA(ctx, new_event(&enc_done));
+            VKT_CUDA(ctx, cudaEventRecord(enc_done, enc));
+            VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, enc_done, 0));
+            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[0]) + size_t(e0) * row_blk0, d_blk, size_t(e1 - e0) * row_blk0,
+                                          cudaMemcpyDeviceToHost, s->stream3));
+            count(ctx, 0, 0, size_t(e1 - e0) * row_blk0);
+        }
+        while(!rc && uploaded < K)// (only if level 0 has no block rows at all -- cannot happen -- or bands were skipped)
+        {
+            rc = upload(uploaded);
+            ++uploaded;
+        }
+        if(rc) { break; }
+        // remaining levels: resize chain, then every level in one set of launches, then the gather
+        const uint8_t *prev = lvl0;
+        uint32_t pw = w0, ph = h0;
         struct Slice
         {
             uint32_t level, r0, r1;
         };
         std::vector<Slice> slices;
         std::vector<DevImage> dev;
-        for(uint32_t l = 0; l < plan.num_levels && !rc; ++l)
+        for(uint32_t l = 1; l < plan.num_levels && !rc; ++l)
         {
             const uint32_t w = plan.level_width[l], h = plan.level_height[l];
             uint8_t *cur = d_lvl + lvl_off[l];
@@ -299,13 +386,15 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             dev.push_back({cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk});
         }
         if(rc) { break; }
-        // every level of the chain in one set of launches, then the gather
-        if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
-        else
+        if(!dev.empty())
         {
-            for(const DevImage &d: dev)
+            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
+            else
             {
-                if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream))) { break; }
+                for(const DevImage &d: dev)
+                {
+                    if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream))) { break; }
+                }
             }
         }
         for(size_t k = 0; k < slices.size() && !rc; ++k)
@@ -321,9 +410,15 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     {
         DeviceSlot *s = ctx->slots[g];
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
-        const cudaError_t e = cudaStreamSynchronize(s->stream);
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        for(cudaStream_t st: {s->stream2, s->stream3, s->stream4, s->stream5})
+        {
+            const cudaError_t e2 = cudaStreamSynchronize(st);
+            if(e == cudaSuccess) { e = e2; }
+        }
         if(e != cudaSuccess && !rc) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
     }
+    for(cudaEvent_t e: events) { cudaEventDestroy(e); }
     return rc;
 }
 
