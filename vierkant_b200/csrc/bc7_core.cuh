@@ -139,6 +139,18 @@ VKT_FN uint32_t vmax_u16x2(uint32_t a, uint32_t b)
 }
 #endif
 
+// Pin a value in a register: stops ptxas from re-deriving it inside a hot loop (it otherwise trades one register for
+// two extra FMA-pipe instructions per use in the selector search).
+#if defined(__CUDA_ARCH__)
+VKT_FN void keep(int &v) { asm volatile("" : "+r"(v)); }
+// a - b computed on the ALU pipe (VIADDMNMX; operands are far below the clamp) given -b: ptxas puts plain subtractions
+// of the selector search on the FMA pipe (IMAD.IADD), which is already the busier one there.
+VKT_FN int sub_alu(int a, int neg_b) { return __viaddmin_s32(a, neg_b, 0x7FFFFFF0); }
+#else
+VKT_FN void keep(int &) {}
+VKT_FN int sub_alu(int a, int neg_b) { return a + neg_b; }
+#endif
+
 VKT_FN float satf(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }// bc7enc.cpp:12-13 (NaN passes through)
 VKT_FN int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 VKT_FN float sqf(float v) { return fmul(v, v); }
@@ -398,6 +410,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
         {
             const Ycc y = to_ycc_packed(pal[j]);
             pl[j] = y.l, pcr[j] = y.cr, pcb[j] = y.cb;
+            keep(pcr[j]), keep(pcb[j]);
             pa[j] = ALPHA ? (int) byte_of(pal[j], 3) : 0;
         }
         if(KEY28)
@@ -407,13 +420,14 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
             for(int k = 0; k < cell.n; ++k)
             {
                 const int i = cell.at(k);
-                const int l2 = L.yl(i), cr2 = L.ycr(i), cb2 = L.ycb(i);
-                const int a2 = ALPHA ? (int) (L.px(i) >> 24) : 0;
+                const Texel t = L.at(i);
+                const int l2 = t.l, ncr2 = -t.cr, ncb2 = -t.cb;
+                const int a2 = ALPHA ? (int) (t.px >> 24) : 0;
                 uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
                 for(int j = 0; j < N; ++j)
                 {
-                    const int dl = (pl[j] - l2) >> 8, dcr = (pcr[j] - cr2) >> 8, dcb = (pcb[j] - cb2) >> 8;
+                    const int dl = (pl[j] - l2) >> 8, dcr = sub_alu(pcr[j], ncr2) >> 8, dcb = sub_alu(pcb[j], ncb2) >> 8;
                     uint32_t e = w0 * (uint32_t) (dl * dl) + (uint32_t) j;
                     e += w1 * (uint32_t) (dcr * dcr);
                     e += w2 * (uint32_t) (dcb * dcb);
