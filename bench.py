@@ -37,11 +37,32 @@ sys.path.insert(0, ROOT)
 
 from vierkant_b200 import synth  # noqa: E402
 
+BYTES_PER_PIXEL = 5.0          # 64 B in + 16 B out per 16-pixel block
+
+# BASELINE.json configs.  The default (and the only one the driver runs) is configs[1]; the others are selectable with
+# --workload for the numbers quoted in DESIGN.md.  ops_per_pixel: algorithmic scalar ops (gcov
+# event counts x per-event costs): opaque defaults 4.7e4 ops/block, alpha defaults 4.7e4, opaque uber 4 + filterbank off
+# 2.1e5; c3 (half alpha, filterbank off: ~36 instead of 28.7 partitions scored) ~5.3e4.
+WORKLOADS = {
+    "c2": dict(base=4096, kind=0, rotate=4, params=dict(), ops_per_pixel=2.9e3,
+               name="4096x4096 RGBA8 opaque albedo-like (synthetic kind 0) + full mip chain, default bc7enc params",
+               params_name="bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"),
+    "c1": dict(base=1024, kind=0, rotate=16, params=dict(), ops_per_pixel=2.9e3,
+               name="1024x1024 RGBA8 noise+gradient (synthetic kind 0) + full mip chain, default bc7enc params",
+               params_name="bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"),
+    "c3": dict(base=8192, kind=1, rotate=1, params=dict(max_partitions=64, mode17_partition_estimation_filterbank=0),
+               ops_per_pixel=3.3e3,
+               name="8192x8192 RGBA8 with alpha gradients (synthetic kind 1: modes 1/5/6/7) + full mip chain, max partitions",
+               params_name="perceptual, 64 partitions, filterbank off (every pattern is a candidate), uber 0"),
+    "c5": dict(base=16384, kind=0, rotate=1,
+               params=dict(uber_level=4, max_partitions=64, mode17_partition_estimation_filterbank=0), ops_per_pixel=1.3e4,
+               name="16384x16384 RGBA8 opaque (synthetic kind 0) + full mip chain, highest quality",
+               params_name="perceptual, uber level 4 (BC7ENC_MAX_UBER_LEVEL), 64 partitions, filterbank off"),
+}
 BASE = 4096
 KIND = 0
-WORKLOAD = "4096x4096 RGBA8 opaque albedo-like (synthetic kind 0) + full mip chain, default bc7enc params"
-OPS_PER_PIXEL = 2.9e3          # algorithmic scalar ops per pixel, opaque blocks, default params
-BYTES_PER_PIXEL = 5.0          # 64 B in + 16 B out per 16-pixel block
+WORKLOAD = WORKLOADS["c2"]["name"]
+OPS_PER_PIXEL = WORKLOADS["c2"]["ops_per_pixel"]
 ROTATE = 4
 
 
@@ -199,7 +220,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--base", type=int, default=BASE, help="level-0 size (default: the BASELINE workload)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default c2 = configs[1])")
+    ap.add_argument("--base", type=int, default=None, help="override the workload's level-0 size (experiments only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -221,9 +243,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    wl = WORKLOADS[args.workload]
+    base = args.base or wl["base"]
+    KIND, ROTATE, OPS_PER_PIXEL = wl["kind"], wl["rotate"], wl["ops_per_pixel"]
+    WORKLOAD = wl["name"] if base == wl["base"] else wl["name"].replace(f"{wl['base']}x{wl['base']}", f"{base}x{base}")
     ctx = capi.BcnContext([local])
-    params = capi.default_params()
-    dims = chain_dims(args.base)
+    params = capi.default_params(**wl["params"])
+    dims = chain_dims(base)
     npix = sum(w * h for w, h in dims)
     nblocks = sum((w // 4) * (h // 4) for w, h in dims)
 
@@ -336,7 +362,7 @@ def main():
             "config": {"workload": WORKLOAD, "levels": len(dims), "blocks_per_step_per_gpu": nblocks,
                        "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world} independent texture chains, one per GPU, no collective",
                        "l2": f"{ROTATE} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
-                       "params": "bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"},
+                       "params": wl["params_name"]},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
                     "api": "vkt_bcn_cuda_compress == vierkant::bcn::compress(): pinned host source image in, stbir-exact resize chain + "
@@ -345,7 +371,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",
                          "frac": achieved / alu_peak, "traffic": None,
-                         "kernel": "bc7_encode_kernel<perceptual> on level 0 (4096x4096)", "kernel_ms": kernel_ms,
+                         "kernel": f"bc7_encode_kernel<perceptual> launch set on level 0 ({base}x{base})", "kernel_ms": kernel_ms,
                          "ops_per_pixel": OPS_PER_PIXEL,
                          "peak_source": f"{props.multi_processor_count} SMs x 4 x 32 lanes x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peak_src} clock)",
                          "sm_mhz_during_run": sm_mhz,
@@ -354,7 +380,7 @@ def main():
                          "hbm": {"achieved_gbs": l0_pix * BYTES_PER_PIXEL / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": f"informational, {peak_src}"}},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
             try:
                 v, info = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", **info}

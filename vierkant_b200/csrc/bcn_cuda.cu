@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -243,10 +244,12 @@ struct DeviceSlot
     vkt_axis_cache *axis_cache = nullptr;
     int device = -1;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;// 2: uploads / second batch lane, 3: downloads
-    cudaStream_t stream4 = nullptr, stream5 = nullptr;                  // encode ping-pong of the pipelined chain
+    cudaStream_t stream4 = nullptr, stream5 = nullptr, stream6 = nullptr;// encode lanes of the pipelined chain (round robin)
     Bc7Tables *d_tables = nullptr;
     void *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
     size_t in_cap = 0, out_cap = 0, tmp_cap = 0;
+    std::vector<cudaEvent_t> event_pool;// ordering events of the pipelined chain (guarded by mtx like the buffers)
+    size_t events_used = 0;
     std::mutex mtx;
 };
 
@@ -480,11 +483,16 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         s->device = dev;
         ctx->slots.push_back(s);
         cudaError_t e = cudaSetDevice(dev);
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking); }
+        // `stream` carries the (cheap) resize kernels of the pipelined chain: highest priority, so that their CTAs are placed
+        // ahead of the pending CTAs of the long encode kernels running on the other lanes
+        int prio_lo = 0, prio_hi = 0;
+        if(e == cudaSuccess) { e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi); }
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream5, cudaStreamNonBlocking); }
+        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream6, cudaStreamNonBlocking); }
         if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
         if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
         if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
@@ -520,7 +528,7 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
                 cudaStreamSynchronize(s->stream);
                 cudaStreamDestroy(s->stream);
             }
-            for(cudaStream_t st: {s->stream3, s->stream4, s->stream5})
+            for(cudaStream_t st: {s->stream3, s->stream4, s->stream5, s->stream6})
             {
                 if(st)
                 {
@@ -533,6 +541,7 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
                 cudaStreamSynchronize(s->stream2);
                 cudaStreamDestroy(s->stream2);
             }
+            for(cudaEvent_t ev: s->event_pool) { cudaEventDestroy(ev); }
             cudaFree(s->d_tables);
             cudaFree(s->d_in);
             cudaFree(s->d_out);

@@ -268,22 +268,56 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     std::vector<std::unique_lock<std::mutex>> locks;
     for(uint32_t g = 0; g < G; ++g) { locks.emplace_back(ctx->slots[g]->mtx); }
     int rc = VKT_BCN_OK;
-    // Level 0 is pipelined in K row bands over several streams per device -- upload (stream2) -> resize (stream) -> encode
-    // (stream4 / stream5 alternating, so the tail wave of one band overlaps the head of the next) -> download (stream3)
-    // -- so that PCIe traffic hides behind the encode kernels; the remaining levels (a quarter of the work) follow as
-    // one launch set.
+    // Level 0 is pipelined in row bands over several streams per device -- upload (stream2) -> resize (stream, high
+    // priority) -> encode (stream4/5/6 round robin, so the tail wave of one band overlaps the heads of the next ones) ->
+    // download (stream3) -- so that PCIe traffic hides behind the encode kernels.  Bands are small at both ends: the first
+    // encode starts after 1/32 of the upload, and the drain at the end of the call is that of a small launch.  The
+    // remaining levels (a quarter of the work) are queued behind the last level-0 resize on the high-priority stream, so
+    // they run in the middle of the band sequence, not after it.
     const uint32_t rows0 = plan.level_height[0] / 4;
-    const uint32_t K = plan.level_num_blocks[0] >= (1u << 18) ? 8u : (plan.level_num_blocks[0] >= (1u << 14) ? 2u : 1u);
-    std::vector<cudaEvent_t> events;
-    auto new_event = [&](cudaEvent_t *e) -> cudaError_t {
-        const cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
-        if(r == cudaSuccess) { events.push_back(*e); }
-        return r;
+    std::vector<uint32_t> band_end;// block-row end of every band of level 0
+    {
+        static const uint8_t kBig[] = {1, 3, 6, 10, 14, 18, 22, 26, 29, 31, 32};// cumulative 32nds
+        static const uint8_t kMid[] = {16, 32};
+        static const uint8_t kOne[] = {32};
+        const bool big = plan.level_num_blocks[0] >= (1u << 18), mid = plan.level_num_blocks[0] >= (1u << 14);
+        const uint8_t *f = big ? kBig : (mid ? kMid : kOne);
+        const size_t nf = big ? sizeof(kBig) : (mid ? sizeof(kMid) : sizeof(kOne));
+        for(size_t k = 0; k < nf; ++k)
+        {
+            const uint32_t e = uint32_t(uint64_t(rows0) * f[k] / 32);
+            if(e > (band_end.empty() ? 0u : band_end.back())) { band_end.push_back(e); }
+        }
+        if(band_end.empty() || band_end.back() != rows0) { band_end.push_back(rows0); }
+    }
+    const uint32_t K = uint32_t(band_end.size());
+    DeviceSlot *ev_slot = nullptr;// events come from the current slot's pool (created once per context, reused by every call)
+    // VKT_BCN_TRACE=1: events carry timestamps and the call prints its device timeline to stderr (diagnostics only)
+    static const bool trace = getenv("VKT_BCN_TRACE") != nullptr;
+    std::vector<std::pair<cudaEvent_t, std::string>> marks;
+    auto new_event = [&](cudaEvent_t *e, const char *what = nullptr, uint32_t k = 0) -> cudaError_t {
+        DeviceSlot *s = ev_slot;
+        if(s->events_used == s->event_pool.size())
+        {
+            cudaEvent_t fresh;
+            const cudaError_t r = cudaEventCreateWithFlags(&fresh, trace ? cudaEventDefault : cudaEventDisableTiming);
+            if(r != cudaSuccess) { return r; }
+            s->event_pool.push_back(fresh);
+        }
+        *e = s->event_pool[s->events_used++];
+        if(trace && what) { marks.emplace_back(*e, std::string(what) + " " + std::to_string(k)); }
+        return cudaSuccess;
+    };
+    auto mark = [&](cudaStream_t st, const char *what, uint32_t k = 0) {
+        if(!trace) { return; }
+        cudaEvent_t e;
+        if(new_event(&e, what, k) == cudaSuccess) { cudaEventRecord(e, st); }
     };
     for(uint32_t g = 0; g < G && !rc; ++g)
     {
         DeviceSlot *s = ctx->slots[g];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
+        ev_slot = s, s->events_used = 0;
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_total))) { break; }
         uint8_t *d_src = static_cast<uint8_t *>(s->d_in), *d_lvl = d_src + align_up(src_bytes, 256);
@@ -297,8 +331,11 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         const size_t src_row = size_t(width) * comps;
         std::vector<uint32_t> up_end(K);
         std::vector<cudaEvent_t> up_done(K);
-        for(uint32_t k = 0; k < K; ++k) { up_end[k] = uint32_t(uint64_t(height) * (k + 1) / K); }
+        // upload band k ends with the last source row the resize of encode band k reads: band k needs uploads 0..k only
+        for(uint32_t k = 0; k < K; ++k) { up_end[k] = (k + 1 == K) ? height : std::min<uint32_t>(height, uint32_t(ay0->last_in[size_t(band_end[k]) * 4 - 1]) + 1u); }
+        for(uint32_t k = 1; k < K; ++k) { up_end[k] = std::max(up_end[k], up_end[k - 1]); }
         uint32_t uploaded = 0;// number of upload bands queued
+        mark(s->stream2, "t0");
         auto upload = [&](uint32_t k) -> int {
             const uint32_t y0 = k ? up_end[k - 1] : 0, y1 = up_end[k];
             if(y1 > y0)
@@ -307,7 +344,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
                                               cudaMemcpyHostToDevice, s->stream2));
                 count(ctx, 0, size_t(y1 - y0) * src_row, 0);
             }
-            VKT_CUDA(ctx, new_event(&up_done[k]));
+            VKT_CUDA(ctx, new_event(&up_done[k], "upload done", k));
             VKT_CUDA(ctx, cudaEventRecord(up_done[k], s->stream2));
             return VKT_BCN_OK;
         };
@@ -316,11 +353,11 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         const size_t row_px0 = size_t(w0) * comps * 4, row_blk0 = size_t(w0 / 4) * 16;
         for(uint32_t k = 0; k < K && !rc; ++k)
         {
-            const uint32_t b0 = uint32_t(uint64_t(rows0) * k / K), b1 = uint32_t(uint64_t(rows0) * (k + 1) / K);// block rows of the band
+            const uint32_t b0 = k ? band_end[k - 1] : 0u, b1 = band_end[k];// block rows of the band
             if(b1 <= b0) { continue; }
             // uploads needed by this band's resize: every source row up to the last tap of its last output row
             const uint32_t need_row = uint32_t(ay0->last_in[size_t(b1) * 4 - 1]);
-            while(uploaded < K && (uploaded == 0 || up_end[uploaded - 1] <= need_row))
+            while(uploaded < K && (uploaded == 0 || up_end[uploaded - 1] <= need_row))// (== uploads 0..k)
             {
                 if((rc = upload(uploaded))) { break; }
                 ++uploaded;
@@ -338,21 +375,23 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             const uint32_t e0 = std::max(b0, own0), e1 = std::min(b1, own1);
             if(e0 >= e1) { continue; }
             cudaEvent_t resized;
-            VKT_CUDA(ctx, new_event(&resized));
+            VKT_CUDA(ctx, new_event(&resized, "resize done", k));
             VKT_CUDA(ctx, cudaEventRecord(resized, s->stream));
-            cudaStream_t enc = (k & 1u) ? s->stream5 : s->stream4;
+            cudaStream_t enc = (k % 3u == 0) ? s->stream4 : ((k % 3u == 1) ? s->stream5 : s->stream6);
             VKT_CUDA(ctx, cudaStreamWaitEvent(enc, resized, 0));
+            mark(enc, "encode start", k);
             uint8_t *d_blk = static_cast<uint8_t *>(s->d_out) + out_off[0] + size_t(e0) * row_blk0;
             if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7(ctx, s, lvl0 + size_t(e0) * row_px0, w0, (e1 - e0) * 4, comps, w0 * comps, params, d_blk, enc); }
             else { rc = launch_bc5(ctx, s, lvl0 + size_t(e0) * row_px0, w0, (e1 - e0) * 4, comps, w0 * comps, d_blk, enc); }
             if(rc) { break; }
             cudaEvent_t enc_done;
-            VKT_CUDA(ctx, new_event(&enc_done));
+            VKT_CUDA(ctx, new_event(&enc_done, "encode done", k));
             VKT_CUDA(ctx, cudaEventRecord(enc_done, enc));
             VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, enc_done, 0));
             VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[0]) + size_t(e0) * row_blk0, d_blk, size_t(e1 - e0) * row_blk0,
                                           cudaMemcpyDeviceToHost, s->stream3));
             count(ctx, 0, 0, size_t(e1 - e0) * row_blk0);
+            mark(s->stream3, "download done", k);
         }
         while(!rc && uploaded < K)// (only if level 0 has no block rows at all -- cannot happen -- or bands were skipped)
         {
@@ -386,6 +425,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             dev.push_back({cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk});
         }
         if(rc) { break; }
+        mark(s->stream, "mip resizes done");
         if(!dev.empty())
         {
             if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
@@ -397,6 +437,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
                 }
             }
         }
+        mark(s->stream, "mip encode done");
         for(size_t k = 0; k < slices.size() && !rc; ++k)
         {
             const Slice &sl = slices[k];
@@ -405,20 +446,28 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
                                           cudaMemcpyDeviceToHost, s->stream));
             count(ctx, 0, 0, bytes);
         }
+        mark(s->stream, "mip download done");
     }
     for(uint32_t g = 0; g < G; ++g)
     {
         DeviceSlot *s = ctx->slots[g];
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
         cudaError_t e = cudaStreamSynchronize(s->stream);
-        for(cudaStream_t st: {s->stream2, s->stream3, s->stream4, s->stream5})
+        for(cudaStream_t st: {s->stream2, s->stream3, s->stream4, s->stream5, s->stream6})
         {
             const cudaError_t e2 = cudaStreamSynchronize(st);
             if(e == cudaSuccess) { e = e2; }
         }
         if(e != cudaSuccess && !rc) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
     }
-    for(cudaEvent_t e: events) { cudaEventDestroy(e); }
+    if(trace && !marks.empty() && G == 1)
+    {
+        for(const auto &m: marks)
+        {
+            float ms = 0.0f;
+            if(cudaEventElapsedTime(&ms, marks[0].first, m.first) == cudaSuccess) { fprintf(stderr, "[vkt trace] %8.3f ms  %s\n", ms, m.second.c_str()); }
+        }
+    }
     return rc;
 }
 
