@@ -91,6 +91,17 @@ def test_compress_known_answers(ctx, known):
         assert "%016x" % synth.fnv1a64_words(allb) == e["fnv1a64"], e
 
 
+def test_compress_big_odd_size_is_banded_and_exact(ctx, port_oracle):
+    """>= 2^18 blocks: level 0 goes through the graded row bands (upload / resize / encode / download pipelined), here with
+    the Catmull-Rom upsample of an odd size (2050 x 2046 -> 2052 x 2048) in front."""
+    img = synth.make_texture(2050, 2046, 1, seed=77)
+    want = port_oracle.compress(img, 1, True, threads=os.cpu_count() or 1)
+    plan, levels = ctx.compress(img, capi.MODE_BC7, True)
+    assert (plan.base_width, plan.base_height, plan.num_levels) == (2052, 2048, len(want["levels"]))
+    for got, ref in zip(levels, want["levels"]):
+        assert np.array_equal(got, ref)
+
+
 def test_compress_with_parameters(ctx, port_oracle):
     from oracle.pyoracle import default_params
     img = synth.make_texture(128, 64, 1, seed=12)

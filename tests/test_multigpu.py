@@ -18,6 +18,17 @@ def multi_ctx(cuda_lib):
     c.close()
 
 
+@pytest.fixture(scope="module")
+def known_2048():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")) as f:
+        for e in json.load(f)["compress"]:
+            if e["size"] == 2048 and e["kind"] == 0:
+                return e["fnv1a64"]
+    pytest.skip("no 2048^2 known answer")
+
+
 def test_encode_rows_split_over_devices(ctx, multi_ctx):
     img = synth.make_texture(1024, 512, 1, seed=3)
     assert multi_ctx.num_devices >= 2
@@ -32,6 +43,17 @@ def test_compress_chain_split_over_devices(ctx, multi_ctx):
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_compress_chain_big_split_over_devices(ctx, multi_ctx, known_2048):
+    """2048^2 + mips (graded band pipeline on every device, each encoding its own block rows): identical to one device
+    and to the reference's hash."""
+    img = synth.make_texture(2048, 2048, 0)
+    _, a = multi_ctx.compress(img, capi.MODE_BC7, True)
+    _, b = ctx.compress(img, capi.MODE_BC7, True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert "%016x" % synth.fnv1a64_words(np.concatenate(a)) == known_2048
 
 
 def test_batch_of_textures_over_devices(ctx, multi_ctx):

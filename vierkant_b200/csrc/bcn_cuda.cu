@@ -262,6 +262,8 @@ struct vkt_bcn_ctx
     std::mutex err_mtx;
     vkt_bcn_stats stats{};
     std::mutex stats_mtx;
+    void *h_stage = nullptr;// pinned gather buffer of the multi-device chain (used with every slot mutex held)
+    size_t stage_cap = 0;
 };
 
 namespace vkt
@@ -519,6 +521,7 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
 void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
 {
     if(!ctx) { return; }
+    if(ctx->h_stage) { cudaFreeHost(ctx->h_stage); }
     for(auto *s: ctx->slots)
     {
         if(cudaSetDevice(s->device) == cudaSuccess)

@@ -274,23 +274,40 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     // encode starts after 1/32 of the upload, and the drain at the end of the call is that of a small launch.  The
     // remaining levels (a quarter of the work) are queued behind the last level-0 resize on the high-priority stream, so
     // they run in the middle of the band sequence, not after it.
-    const uint32_t rows0 = plan.level_height[0] / 4;
-    std::vector<uint32_t> band_end;// block-row end of every band of level 0
+    struct Band
     {
+        uint32_t y0, y1;// pixel rows of level 0
+        bool encode;    // false: halo rows, resized here only because this device's slices of the next levels read them
+    };
+    // graded split of the block rows [r0, r1): 1, 2, 3, 4 ... 4, 3, 2, 1 thirty-seconds when there is enough work
+    auto graded = [&](uint32_t r0, uint32_t r1, std::vector<Band> &out) {
         static const uint8_t kBig[] = {1, 3, 6, 10, 14, 18, 22, 26, 29, 31, 32};// cumulative 32nds
         static const uint8_t kMid[] = {16, 32};
         static const uint8_t kOne[] = {32};
-        const bool big = plan.level_num_blocks[0] >= (1u << 18), mid = plan.level_num_blocks[0] >= (1u << 14);
+        const uint64_t blocks = uint64_t(r1 - r0) * (plan.level_width[0] / 4);
+        const bool big = blocks >= (1u << 18), mid = blocks >= (1u << 14);
         const uint8_t *f = big ? kBig : (mid ? kMid : kOne);
         const size_t nf = big ? sizeof(kBig) : (mid ? sizeof(kMid) : sizeof(kOne));
+        uint32_t prev = r0;
         for(size_t k = 0; k < nf; ++k)
         {
-            const uint32_t e = uint32_t(uint64_t(rows0) * f[k] / 32);
-            if(e > (band_end.empty() ? 0u : band_end.back())) { band_end.push_back(e); }
+            const uint32_t e = (k + 1 == nf) ? r1 : r0 + uint32_t(uint64_t(r1 - r0) * f[k] / 32);
+            if(e > prev) { out.push_back({prev * 4, e * 4, true}), prev = e; }
         }
-        if(band_end.empty() || band_end.back() != rows0) { band_end.push_back(rows0); }
+    };
+    // Several devices: levels [0, M) are "sliced" -- every device resizes and encodes its own block rows of each, from
+    // just the source rows those reach through the filter taps (own rows plus a halo that grows by ~5 rows per level).
+    // Slicing stops where the halo would outgrow the slice (level height < 128 rows per device): the small levels
+    // [M, L) are all done by device 0, from level M-1 gathered through a pinned host buffer (<= a few hundred KB).
+    const uint32_t L = plan.num_levels;
+    uint32_t M = L, Geff = G;
+    if(G > 1)
+    {
+        M = 0;
+        while(M < L && plan.level_height[M] / 4 >= G * 4 && plan.level_height[M] >= 128u * G) { ++M; }
+        if(M == 0) { Geff = 1, M = L; }// too small to slice: device 0 does the whole chain
     }
-    const uint32_t K = uint32_t(band_end.size());
+    const bool tail = M < L;
     DeviceSlot *ev_slot = nullptr;// events come from the current slot's pool (created once per context, reused by every call)
     // VKT_BCN_TRACE=1: events carry timestamps and the call prints its device timeline to stderr (diagnostics only)
     static const bool trace = getenv("VKT_BCN_TRACE") != nullptr;
@@ -313,7 +330,21 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         cudaEvent_t e;
         if(new_event(&e, what, k) == cudaSuccess) { cudaEventRecord(e, st); }
     };
-    for(uint32_t g = 0; g < G && !rc; ++g)
+    std::vector<cudaEvent_t> gathered(Geff, nullptr);
+    size_t gather_row_bytes = 0;
+    if(tail)
+    {
+        gather_row_bytes = size_t(plan.level_width[M - 1]) * comps;
+        const size_t need = gather_row_bytes * plan.level_height[M - 1];
+        if(ctx->stage_cap < need)
+        {
+            if(ctx->h_stage) { cudaFreeHost(ctx->h_stage); }
+            ctx->h_stage = nullptr, ctx->stage_cap = 0;
+            VKT_CUDA(ctx, cudaHostAlloc(&ctx->h_stage, need, cudaHostAllocPortable));
+            ctx->stage_cap = need;
+        }
+    }
+    for(uint32_t g = 0; g < Geff && !rc; ++g)
     {
         DeviceSlot *s = ctx->slots[g];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
@@ -321,63 +352,97 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_total))) { break; }
         uint8_t *d_src = static_cast<uint8_t *>(s->d_in), *d_lvl = d_src + align_up(src_bytes, 256);
-        const DeviceAxis *ay0 = nullptr;
-        if((rc = get_axis(ctx, s, int(height), int(plan.level_height[0]), &ay0))) { break; }
-        // this device's block rows of level 0
-        uint32_t own0, own1;
-        if(rows0 < G * 4) { own0 = (0 % G == g) ? 0 : rows0, own1 = rows0; }
-        else { own0 = uint32_t(uint64_t(rows0) * g / G), own1 = uint32_t(uint64_t(rows0) * (g + 1) / G); }
-        // source-row bands of the upload
+        // vertical tap ranges of every sliced level: ay[l] maps rows of level l-1 (l == 0: the source) to rows of level l
+        std::vector<const DeviceAxis *> ay(M, nullptr);
+        for(uint32_t l = 0; l < M && !rc; ++l) { rc = get_axis(ctx, s, int(l ? plan.level_height[l - 1] : height), int(plan.level_height[l]), &ay[l]); }
+        if(rc) { break; }
+        // own[l]: this device's block rows of level l;  need[l]: the pixel rows of level l it has to produce (own rows
+        // plus whatever its rows of level l+1 read)
+        std::vector<std::pair<uint32_t, uint32_t>> own(M), need(M);
+        for(uint32_t l = 0; l < M; ++l)
+        {
+            const uint32_t rows = plan.level_height[l] / 4;
+            own[l] = {uint32_t(uint64_t(rows) * g / Geff), uint32_t(uint64_t(rows) * (g + 1) / Geff)};
+        }
+        for(uint32_t l = M; l-- > 0;)
+        {
+            need[l] = {own[l].first * 4, own[l].second * 4};
+            if(l + 1 < M)
+            {
+                uint32_t lo = need[l].first, hi = need[l].second;
+                for(uint32_t y = need[l + 1].first; y < need[l + 1].second; ++y)
+                {
+                    lo = std::min(lo, uint32_t(ay[l + 1]->first_in[y])), hi = std::max(hi, uint32_t(ay[l + 1]->last_in[y]) + 1u);
+                }
+                need[l] = {lo, std::min(hi, plan.level_height[l])};
+            }
+        }
+        const DeviceAxis *ay0 = ay[0];
+        // This device's bands of level 0, in processing order: its own block rows first (graded, encoded), then the halo
+        // rows above and below (resized only).  Source rows are uploaded in the same order, each band fetching just the
+        // rows its resize taps reach that are not on the device yet.
+        std::vector<Band> bands;
+        graded(own[0].first, own[0].second, bands);
+        if(need[0].second > own[0].second * 4) { bands.push_back({own[0].second * 4, need[0].second, false}); }
+        if(need[0].first < own[0].first * 4) { bands.push_back({need[0].first, own[0].first * 4, false}); }
+        const uint32_t K = uint32_t(bands.size());
         const size_t src_row = size_t(width) * comps;
-        std::vector<uint32_t> up_end(K);
-        std::vector<cudaEvent_t> up_done(K);
-        // upload band k ends with the last source row the resize of encode band k reads: band k needs uploads 0..k only
-        for(uint32_t k = 0; k < K; ++k) { up_end[k] = (k + 1 == K) ? height : std::min<uint32_t>(height, uint32_t(ay0->last_in[size_t(band_end[k]) * 4 - 1]) + 1u); }
-        for(uint32_t k = 1; k < K; ++k) { up_end[k] = std::max(up_end[k], up_end[k - 1]); }
-        uint32_t uploaded = 0;// number of upload bands queued
+        std::vector<std::pair<uint32_t, uint32_t>> have;// disjoint source-row intervals already queued for upload
+        std::vector<cudaEvent_t> ready(K, nullptr);     // recorded on the upload stream once band k's source rows are queued
+        std::vector<char> queued(K, 0);
         mark(s->stream2, "t0");
         auto upload = [&](uint32_t k) -> int {
-            const uint32_t y0 = k ? up_end[k - 1] : 0, y1 = up_end[k];
-            if(y1 > y0)
+            if(queued[k]) { return VKT_BCN_OK; }
+            queued[k] = 1;
+            uint32_t lo = height, hi = 0;
+            for(uint32_t y = bands[k].y0; y < bands[k].y1; ++y) { lo = std::min(lo, uint32_t(ay0->first_in[y])), hi = std::max(hi, uint32_t(ay0->last_in[y]) + 1u); }
+            hi = std::min(hi, height);
+            // subtract what is already there
+            std::vector<std::pair<uint32_t, uint32_t>> todo;
+            if(lo < hi) { todo.push_back({lo, hi}); }
+            for(const auto &iv: have)
             {
-                VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(y0) * src_row, pixels + size_t(y0) * src_row, size_t(y1 - y0) * src_row,
-                                              cudaMemcpyHostToDevice, s->stream2));
-                count(ctx, 0, size_t(y1 - y0) * src_row, 0);
+                std::vector<std::pair<uint32_t, uint32_t>> next;
+                for(const auto &t: todo)
+                {
+                    if(iv.second <= t.first || iv.first >= t.second)
+                    {
+                        next.push_back(t);
+                        continue;
+                    }
+                    if(t.first < iv.first) { next.push_back({t.first, iv.first}); }
+                    if(iv.second < t.second) { next.push_back({iv.second, t.second}); }
+                }
+                todo.swap(next);
             }
-            VKT_CUDA(ctx, new_event(&up_done[k], "upload done", k));
-            VKT_CUDA(ctx, cudaEventRecord(up_done[k], s->stream2));
+            for(const auto &t: todo)
+            {
+                VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(t.first) * src_row, pixels + size_t(t.first) * src_row,
+                                              size_t(t.second - t.first) * src_row, cudaMemcpyHostToDevice, s->stream2));
+                count(ctx, 0, size_t(t.second - t.first) * src_row, 0);
+                have.push_back(t);
+            }
+            VKT_CUDA(ctx, new_event(&ready[k], "upload done", k));
+            VKT_CUDA(ctx, cudaEventRecord(ready[k], s->stream2));
             return VKT_BCN_OK;
         };
         const uint32_t w0 = plan.level_width[0], h0 = plan.level_height[0];
         uint8_t *lvl0 = d_lvl + lvl_off[0];
         const size_t row_px0 = size_t(w0) * comps * 4, row_blk0 = size_t(w0 / 4) * 16;
+        uint32_t lane = 0;
         for(uint32_t k = 0; k < K && !rc; ++k)
         {
-            const uint32_t b0 = k ? band_end[k - 1] : 0u, b1 = band_end[k];// block rows of the band
-            if(b1 <= b0) { continue; }
-            // uploads needed by this band's resize: every source row up to the last tap of its last output row
-            const uint32_t need_row = uint32_t(ay0->last_in[size_t(b1) * 4 - 1]);
-            while(uploaded < K && (uploaded == 0 || up_end[uploaded - 1] <= need_row))// (== uploads 0..k)
-            {
-                if((rc = upload(uploaded))) { break; }
-                ++uploaded;
-            }
-            if(rc) { break; }
-            if(k + 1 < K && uploaded < K)// keep the link busy: queue the next upload before this band's kernels
-            {
-                if((rc = upload(uploaded))) { break; }
-                ++uploaded;
-            }
-            uint32_t need_band = 0;
-            while(need_band + 1 < K && up_end[need_band] <= need_row) { ++need_band; }
-            VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, up_done[need_band], 0));
-            if((rc = resize_device(ctx, s, d_src, width, height, comps, lvl0, w0, h0, s->stream, b0 * 4, b1 * 4))) { break; }
-            const uint32_t e0 = std::max(b0, own0), e1 = std::min(b1, own1);
-            if(e0 >= e1) { continue; }
+            if((rc = upload(k))) { break; }
+            if(k + 1 < K && (rc = upload(k + 1))) { break; }// keep the link busy: queue the next upload before this band's kernels
+            VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, ready[k], 0));
+            if((rc = resize_device(ctx, s, d_src, width, height, comps, lvl0, w0, h0, s->stream, bands[k].y0, bands[k].y1))) { break; }
+            if(!bands[k].encode) { continue; }
+            const uint32_t e0 = bands[k].y0 / 4, e1 = bands[k].y1 / 4;
             cudaEvent_t resized;
             VKT_CUDA(ctx, new_event(&resized, "resize done", k));
             VKT_CUDA(ctx, cudaEventRecord(resized, s->stream));
-            cudaStream_t enc = (k % 3u == 0) ? s->stream4 : ((k % 3u == 1) ? s->stream5 : s->stream6);
+            cudaStream_t enc = (lane % 3u == 0) ? s->stream4 : ((lane % 3u == 1) ? s->stream5 : s->stream6);
+            ++lane;
             VKT_CUDA(ctx, cudaStreamWaitEvent(enc, resized, 0));
             mark(enc, "encode start", k);
             uint8_t *d_blk = static_cast<uint8_t *>(s->d_out) + out_off[0] + size_t(e0) * row_blk0;
@@ -393,60 +458,107 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             count(ctx, 0, 0, size_t(e1 - e0) * row_blk0);
             mark(s->stream3, "download done", k);
         }
-        while(!rc && uploaded < K)// (only if level 0 has no block rows at all -- cannot happen -- or bands were skipped)
-        {
-            rc = upload(uploaded);
-            ++uploaded;
-        }
         if(rc) { break; }
-        // remaining levels: resize chain, then every level in one set of launches, then the gather
-        const uint8_t *prev = lvl0;
-        uint32_t pw = w0, ph = h0;
+        // sliced mip levels: resize the needed rows, then this device's block rows of every level in one set of launches
         struct Slice
         {
             uint32_t level, r0, r1;
         };
         std::vector<Slice> slices;
         std::vector<DevImage> dev;
-        for(uint32_t l = 1; l < plan.num_levels && !rc; ++l)
+        for(uint32_t l = 1; l < M && !rc; ++l)
         {
             const uint32_t w = plan.level_width[l], h = plan.level_height[l];
             uint8_t *cur = d_lvl + lvl_off[l];
-            if((rc = resize_device(ctx, s, prev, pw, ph, comps, cur, w, h, s->stream))) { break; }
-            prev = cur, pw = w, ph = h;
-            // this device's block rows of the level (levels with few rows go to one device, rotating)
-            const uint32_t rows = h / 4;
-            uint32_t r0, r1;
-            if(rows < G * 4) { r0 = (l % G == g) ? 0 : rows, r1 = rows; }
-            else { r0 = uint32_t(uint64_t(rows) * g / G), r1 = uint32_t(uint64_t(rows) * (g + 1) / G); }
-            if(r0 >= r1) { continue; }
+            if((rc = resize_device(ctx, s, d_lvl + lvl_off[l - 1], plan.level_width[l - 1], plan.level_height[l - 1], comps, cur, w, h, s->stream,
+                                   need[l].first, need[l].second)))
+            {
+                break;
+            }
+            const uint32_t r0 = own[l].first, r1 = own[l].second;
             const size_t row_px = size_t(w) * comps * 4, row_blk = size_t(w / 4) * 16;
             slices.push_back({l, r0, r1});
             dev.push_back({cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk});
         }
         if(rc) { break; }
         mark(s->stream, "mip resizes done");
-        if(!dev.empty())
+        if(tail && g > 0)
         {
-            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
-            else
+            // this device's rows of level M-1 -> the pinned gather buffer (device 0 continues the chain from there)
+            const size_t off = size_t(own[M - 1].first) * 4 * gather_row_bytes, bytes = size_t(own[M - 1].second - own[M - 1].first) * 4 * gather_row_bytes;
+            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(ctx->h_stage) + off, d_lvl + lvl_off[M - 1] + off, bytes, cudaMemcpyDeviceToHost, s->stream));
+            count(ctx, 0, 0, bytes);
+            VKT_CUDA(ctx, new_event(&gathered[g]));
+            VKT_CUDA(ctx, cudaEventRecord(gathered[g], s->stream));
+        }
+        auto encode_and_fetch = [&]() -> int {
+            if(!dev.empty())
             {
-                for(const DevImage &d: dev)
+                if(mode == VKT_BCN_MODE_BC7)
                 {
-                    if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream))) { break; }
+                    const int r = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream);
+                    if(r) { return r; }
+                }
+                else
+                {
+                    for(const DevImage &d: dev)
+                    {
+                        const int r = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream);
+                        if(r) { return r; }
+                    }
                 }
             }
-        }
-        mark(s->stream, "mip encode done");
-        for(size_t k = 0; k < slices.size() && !rc; ++k)
+            mark(s->stream, "mip encode done");
+            for(size_t k = 0; k < slices.size(); ++k)
+            {
+                const Slice &sl = slices[k];
+                const size_t row_blk = size_t(plan.level_width[sl.level] / 4) * 16, bytes = size_t(sl.r1 - sl.r0) * row_blk;
+                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[sl.level]) + size_t(sl.r0) * row_blk, dev[k].d_out, bytes,
+                                              cudaMemcpyDeviceToHost, s->stream));
+                count(ctx, 0, 0, bytes);
+            }
+            mark(s->stream, "mip download done");
+            return VKT_BCN_OK;
+        };
+        if((rc = encode_and_fetch())) { break; }
+    }
+    if(tail && !rc)
+    {
+        // small levels [M, L) on device 0: wait for every device's rows of level M-1, fetch them, continue the chain
+        DeviceSlot *s = ctx->slots[0];
+        VKT_CUDA(ctx, cudaSetDevice(s->device));
+        ev_slot = s;
+        uint8_t *d_lvl = static_cast<uint8_t *>(s->d_in) + align_up(src_bytes, 256);
+        for(uint32_t g = 1; g < Geff; ++g) { VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, gathered[g], 0)); }
         {
-            const Slice &sl = slices[k];
-            const size_t row_blk = size_t(plan.level_width[sl.level] / 4) * 16, bytes = size_t(sl.r1 - sl.r0) * row_blk;
-            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[sl.level]) + size_t(sl.r0) * row_blk, dev[k].d_out, bytes,
-                                          cudaMemcpyDeviceToHost, s->stream));
+            // rows of the other devices only (device 0's own rows are in place and may still be read by its encode kernels)
+            const size_t off = size_t(plan.level_height[M - 1] / 4 * 1 / Geff) * 4 * gather_row_bytes;
+            const size_t total = gather_row_bytes * plan.level_height[M - 1];
+            VKT_CUDA(ctx, cudaMemcpyAsync(d_lvl + lvl_off[M - 1] + off, static_cast<uint8_t *>(ctx->h_stage) + off, total - off, cudaMemcpyHostToDevice, s->stream));
+            count(ctx, 0, total - off, 0);
+        }
+        std::vector<DevImage> dev;
+        for(uint32_t l = M; l < L && !rc; ++l)
+        {
+            const uint32_t w = plan.level_width[l], h = plan.level_height[l];
+            uint8_t *cur = d_lvl + lvl_off[l];
+            if((rc = resize_device(ctx, s, d_lvl + lvl_off[l - 1], plan.level_width[l - 1], plan.level_height[l - 1], comps, cur, w, h, s->stream))) { break; }
+            dev.push_back({cur, w, h, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l]});
+        }
+        if(!rc && mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, s->stream); }
+        else if(!rc)
+        {
+            for(const DevImage &d: dev)
+            {
+                if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, s->stream))) { break; }
+            }
+        }
+        for(uint32_t l = M; l < L && !rc; ++l)
+        {
+            const size_t bytes = size_t(plan.level_num_blocks[l]) * 16;
+            VKT_CUDA(ctx, cudaMemcpyAsync(level_blocks[l], static_cast<uint8_t *>(s->d_out) + out_off[l], bytes, cudaMemcpyDeviceToHost, s->stream));
             count(ctx, 0, 0, bytes);
         }
-        mark(s->stream, "mip download done");
     }
     for(uint32_t g = 0; g < G; ++g)
     {
