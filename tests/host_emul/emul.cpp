@@ -13,7 +13,35 @@
 #include "../../vierkant_b200/csrc/bc7_params.h"
 #include "../../vierkant_b200/csrc/resize_axis.h"
 
+// the uber-free instantiation whenever the parameters allow it, as the CUDA dispatch does
+template<bool PERC, bool KEY28, bool ALPHA>
+static void enc(const vkt::Bc7Tables &tables, const vkt::Bc7KernelParams &kp, vkt::Lane<1> lane, uint32_t blk[4])
+{
+    if(kp.uber_level == 0) { vkt::encode_block<PERC, KEY28, ALPHA, false, 1>(tables, kp, lane, blk); }
+    else { vkt::encode_block<PERC, KEY28, ALPHA, true, 1>(tables, kp, lane, blk); }
+}
+
 extern "C" {
+
+// number of (max, ly, hy) cells whose compile-time uber selector map differs from the reference's float expression
+int emul_uber_map_mismatches()
+{
+    const vkt::UberMaps um = vkt::make_uber_maps();
+    int bad = 0;
+    for(int k = 0; k < 3; ++k)
+    {
+        const int max_sel = (k == 0) ? 3 : (k == 1) ? 7 : 15;
+        const uint64_t live = (max_sel == 15) ? ~0ull : ((1ull << (4 * (max_sel + 1))) - 1ull);
+        for(int ly = -2; ly <= 1; ++ly)
+        {
+            for(int hy = max_sel - 1; hy <= max_sel + 2; ++hy)
+            {
+                bad += (um.m[k][ly + 2][hy - (max_sel - 1)] & live) != (vkt::bc7_uber_map_reference(max_sel, ly, hy) & live);
+            }
+        }
+    }
+    return bad;
+}
 
 int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7_params *params, uint8_t *out, int threads)
 {
@@ -43,14 +71,14 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
             const int sel = (perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
             switch(sel)
             {
-                case 7: vkt::encode_block<true, true, true, 1>(tables, kp, lane, blk); break;
-                case 6: vkt::encode_block<true, true, false, 1>(tables, kp, lane, blk); break;
-                case 5: vkt::encode_block<true, false, true, 1>(tables, kp, lane, blk); break;
-                case 4: vkt::encode_block<true, false, false, 1>(tables, kp, lane, blk); break;
-                case 3: vkt::encode_block<false, true, true, 1>(tables, kp, lane, blk); break;
-                case 2: vkt::encode_block<false, true, false, 1>(tables, kp, lane, blk); break;
-                case 1: vkt::encode_block<false, false, true, 1>(tables, kp, lane, blk); break;
-                default: vkt::encode_block<false, false, false, 1>(tables, kp, lane, blk); break;
+                case 7: enc<true, true, true>(tables, kp, lane, blk); break;
+                case 6: enc<true, true, false>(tables, kp, lane, blk); break;
+                case 5: enc<true, false, true>(tables, kp, lane, blk); break;
+                case 4: enc<true, false, false>(tables, kp, lane, blk); break;
+                case 3: enc<false, true, true>(tables, kp, lane, blk); break;
+                case 2: enc<false, true, false>(tables, kp, lane, blk); break;
+                case 1: enc<false, false, true>(tables, kp, lane, blk); break;
+                default: enc<false, false, false>(tables, kp, lane, blk); break;
             }
             memcpy(out + 16 * b, blk, 16);
         }

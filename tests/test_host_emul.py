@@ -36,7 +36,14 @@ def emul():
         assert lib.emul_resize_u8(img.ctypes.data, w, h, c, out.ctypes.data, ow, oh) == 0
         return out
     encode.resize = resize
+    encode.lib = lib
     return encode
+
+
+def test_uber_selector_maps_match_reference_expression(emul):
+    """bc7_core.cuh generates the uber-level selector rescaling table with integer arithmetic at compile time; it must be
+    the reference's float expression (bc7enc.cpp:1399) for every (max selector, ly, hy, selector)."""
+    assert emul.lib.emul_uber_map_mismatches() == 0
 
 
 @pytest.mark.parametrize("case", sorted(PARAM_CASES))

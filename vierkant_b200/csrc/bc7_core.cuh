@@ -50,12 +50,100 @@ namespace vkt
 #define VKT_ORDER_INIT                                                                                                         \
     {0,  13, 1,  2,  15, 14, 10, 16, 3,  23, 26, 6,  7,  21, 19, 29, 8,  4,  9,  20, 5,  31, 22, 17, 18, 11, 12, 30, 24, 25, 28, 27, \
      32, 33, 34, 45, 46, 51, 49, 50, 48, 38, 39, 37, 53, 52, 54, 36, 57, 58, 55, 41, 40, 42, 43, 59, 44, 56, 47, 35, 60, 63, 62, 61}
+// Estimator work lists (the same data as Bc7Tables::est_idx / est_n0), generated at compile time: texel indices of
+// subset 0 (ascending) followed by those of subset 1, and |subset 0|.
+struct EstLists
+{
+    uint8_t idx[64][16];
+    uint32_t n0[64];
+};
+constexpr EstLists make_est_lists()
+{
+    constexpr uint32_t part2[64] = VKT_PART2_INIT;
+    EstLists t{};
+    for(int p = 0; p < 64; ++p)
+    {
+        int n = 0;
+        for(int sub = 0; sub < 2; ++sub)
+        {
+            for(int i = 0; i < 16; ++i)
+            {
+                if((int) ((part2[p] >> i) & 1u) == sub) { t.idx[p][n++] = (uint8_t) i; }
+            }
+            if(sub == 0) { t.n0[p] = (uint32_t) n; }
+        }
+    }
+    return t;
+}
+// The same lists as texel PAIRS, the unit of the estimator's loops: pairs [0, n[p] & 255) walk subset 0, pairs
+// [n[p] & 255, n[p] >> 8) subset 1; an odd subset ends with a pair that names its last texel twice (i0 == i1).
+struct EstPair
+{
+    uint32_t i0, i1;
+};
+struct EstTrips
+{
+    EstPair t[64][10];// at most (n0 + 1) / 2 + (n1 + 1) / 2 = 9 pairs
+    uint32_t n[64];
+};
+constexpr EstTrips make_est_trips()
+{
+    const EstLists l = make_est_lists();
+    EstTrips t{};
+    for(int p = 0; p < 64; ++p)
+    {
+        int m = 0;
+        const int n0 = (int) l.n0[p];
+        for(int k = 0; k < n0; k += 2) { t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < n0) ? k + 1 : k], ++m; }
+        const int m0 = m;
+        for(int k = n0; k < 16; k += 2) { t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < 16) ? k + 1 : k], ++m; }
+        t.n[p] = (uint32_t) m0 | ((uint32_t) m << 8);
+    }
+    return t;
+}
+// Uber-level selector rescaling (bc7enc.cpp:1381-1410): nibble s of m[k][ly + 2][hy - (max - 1)] is
+// clamp(floor(max * (s - ly) / (hy - ly) + .5f), 0, max) for max = 3, 7, 15 (k = 0, 1, 2), ly in [-2, 1], hy in
+// [max - 1, max + 2].  Generated with integer arithmetic -- floor((2 * num + den) / (2 * den)): the float expression
+// cannot land on the other side of an integer, its operands being integers below 2^8 -- and checked against the
+// reference's float expression when a context is created (bc7_tables.cpp).
+struct UberMaps
+{
+    uint64_t m[3][4][4];
+};
+constexpr UberMaps make_uber_maps()
+{
+    UberMaps t{};
+    for(int k = 0; k < 3; ++k)
+    {
+        const int max_sel = (k == 0) ? 3 : (k == 1) ? 7 : 15;
+        for(int ly = -2; ly <= 1; ++ly)
+        {
+            for(int hy = max_sel - 1; hy <= max_sel + 2; ++hy)
+            {
+                uint64_t map = 0;
+                for(int sel = 0; sel <= max_sel; ++sel)
+                {
+                    const int num = 2 * max_sel * (sel - ly) + (hy - ly), den = 2 * (hy - ly);// den > 0
+                    int v = (num >= 0) ? num / den : -((-num + den - 1) / den);          // floor
+                    v = v < 0 ? 0 : (v > max_sel ? max_sel : v);
+                    map |= (uint64_t) v << (4 * sel);
+                }
+                t.m[k][ly + 2][hy - (max_sel - 1)] = map;
+            }
+        }
+    }
+    return t;
+}
 #if defined(__CUDACC__)
+__constant__ UberMaps c_uber = make_uber_maps();
 __constant__ uint32_t c_part2[64] = VKT_PART2_INIT;// bc7enc.cpp:60-70 packed: bit i = subset of texel i
 __constant__ uint32_t c_order[64] = VKT_ORDER_INIT;// bc7enc.cpp:1765-1775
+__constant__ EstTrips c_trips = make_est_trips();
 #endif
 static const uint32_t h_part2[64] = VKT_PART2_INIT;
 static const uint32_t h_order[64] = VKT_ORDER_INIT;
+static const EstTrips h_trips = make_est_trips();
+static const UberMaps h_uber = make_uber_maps();
 #if defined(__CUDA_ARCH__)
 #define VKT_UTAB(name) c_##name
 #else
@@ -763,7 +851,9 @@ VKT_FN void least_squares(const Bc7Tables &T, Lane<STRIDE> L, CellRef cell, uint
 
 // ---------------------------------------------------------------------------------------------------- color_cell_compression
 // bc7enc.cpp:1101-1441
-template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
+// UBER == false compiles the search without the uber-level stages (P.uber_level must be 0): the default-parameter
+// kernels then carry only the two stages they execute, which keeps their working set of instructions small.
+template<int MODE, bool ALPHA, bool PERC, bool KEY28, bool UBER, int STRIDE>
 VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, Cell &out)
 {
     typedef ModeTraits<MODE> M;
@@ -968,13 +1058,12 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             }
             else
             {
-                const float den = fsub((float) hy, (float) ly);
+                // clampf(floorf(max * (s - ly) / (hy - ly) + .5f), 0, max) per selector, bc7enc.cpp:1399, from the table
+                const uint64_t map = VKT_UTAB(uber).m[(M::N == 4) ? 0 : (M::N == 8) ? 1 : 2][ly + 2][hy - (max_sel_v - 1)];
                 for(int k = 0; k < n; ++k)
                 {
-                    const float s = (float) ((uint32_t) (base >> (4 * k)) & 15u);
-                    float v = floorf(fadd(fdiv(fmul((float) max_sel_v, fsub(s, (float) ly)), den), .5f));
-                    v = v < 0.0f ? 0.0f : (v > (float) max_sel_v ? (float) max_sel_v : v);
-                    trial |= (uint64_t) (uint32_t) f2i(v) << (4 * k);
+                    const uint32_t s4 = (uint32_t) (base >> (4 * k)) & 15u;
+                    trial |= (uint64_t) ((uint32_t) (map >> (4 * s4)) & 15u) << (4 * k);
                 }
             }
             least_squares<MODE, ALPHA, STRIDE>(T, L, cell, trial, xl, xh);
@@ -985,12 +1074,12 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
         if(stage == 0)
         {
             if(P.try_least_squares) { stage = 1; }
-            else if(P.uber_level > 0) { stage = 2; }
+            else if(UBER && P.uber_level > 0) { stage = 2; }
             else { break; }
         }
         else if(stage == 1)
         {
-            if(P.uber_level > 0) { stage = 2; }
+            if(UBER && P.uber_level > 0) { stage = 2; }
             else { break; }
         }
         else if(stage < 4) { ++stage; }
@@ -1079,27 +1168,43 @@ VKT_FN uint32_t estimate_texel(const Bc7KernelParams &P, const Texel t, uint32_t
     return e;
 }
 
-template<bool M7, bool PERC, bool KEY28, int STRIDE>
+// UNI: `part` is warp-uniform (lists from __constant__ memory, uniform loop control); otherwise lane-varying (shared memory).
+template<bool M7, bool PERC, bool KEY28, bool UNI, int STRIDE>
 VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part)
 {
     constexpr int N = M7 ? 4 : 8;
-    const uint8_t *order = T.est_idx[part];
+    // UNI: texel pairs from __constant__ memory (one 64-bit broadcast load per trip, no index arithmetic)
+    const EstPair *trips = VKT_UTAB(trips).t[UNI ? part : 0];
+    const uint32_t tn = VKT_UTAB(trips).n[UNI ? part : 0];
+    const uint8_t *order = T.est_idx[part];// !UNI (lane-varying partition) and the wide-error path
     const int n0 = (int) T.est_n0[part];
     uint64_t total = 0;
 #pragma unroll 1
     for(int s = 0; s < 2; ++s)
     {
-        const int k0 = s ? n0 : 0, k1 = s ? 16 : n0;
+        const int k0 = s ? n0 : 0, k1 = s ? 16 : n0;                                           // !UNI: texel positions
+        const uint32_t q0 = s ? (tn & 255u) : 0u, q1 = s ? (tn >> 8) : (tn & 255u);// UNI: pair positions
         // pass 1: bounding box, 16x2 SIMD lanes (r | g << 16) and (b | a << 16); an odd tail repeats its last texel
         uint32_t l_rg = 0x00FF00FFu, l_ba = 0x00FF00FFu, h_rg = 0u, h_ba = 0u;
-#pragma unroll 1
-        for(int k = k0; k < k1; k += 2)
-        {
-            const uint32_t v0 = L.px(order[k]), v1 = L.px(order[(k + 1 < k1) ? k + 1 : k]);
+        auto grow = [&](uint32_t v0, uint32_t v1) {
             const uint32_t rg0 = prmt(v0, 0u, 0x4140u), ba0 = prmt(v0, 0u, 0x4342u);
             const uint32_t rg1 = prmt(v1, 0u, 0x4140u), ba1 = prmt(v1, 0u, 0x4342u);
             l_rg = vmin_u16x2(l_rg, vmin_u16x2(rg0, rg1)), h_rg = vmax_u16x2(h_rg, vmax_u16x2(rg0, rg1));
             l_ba = vmin_u16x2(l_ba, vmin_u16x2(ba0, ba1)), h_ba = vmax_u16x2(h_ba, vmax_u16x2(ba0, ba1));
+        };
+        if(UNI)
+        {
+#pragma unroll 1
+            for(uint32_t q = q0; q < q1; ++q)
+            {
+                const EstPair w = trips[q];
+                grow(L.px((int) w.i0), L.px((int) w.i1));
+            }
+        }
+        else
+        {
+#pragma unroll 1
+            for(int k = k0; k < k1; k += 2) { grow(L.px(order[k]), L.px(order[(k + 1 < k1) ? k + 1 : k])); }
         }
         // palette: lo*(64-w) + hi*w + 32 = 64*lo + (hi-lo)*w + 32 per 16-bit lane (<= 16352: no carries between lanes)
         const uint32_t ax_rg = h_rg - l_rg, ax_ba = h_ba - l_ba;// hi >= lo per lane (subsets are never empty)
@@ -1129,14 +1234,28 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
         if(KEY28)
         {
             uint32_t sum = 0;// every term < 2^28 (host-checked), at most 16 terms
-#pragma unroll 1
-            for(int k = k0; k < k1; k += 2)
+            if(UNI)
             {
-                const bool two = (k + 1 < k1);
-                const Texel t0 = L.at(order[k]), t1 = L.at(order[two ? k + 1 : k]);
-                const uint32_t e0 = estimate_texel<M7, PERC, N>(P, t0, axb, pal, thr);
-                const uint32_t e1 = estimate_texel<M7, PERC, N>(P, t1, axb, pal, thr);
-                sum += e0 + (two ? e1 : 0u);
+#pragma unroll 1
+                for(uint32_t q = q0; q < q1; ++q)
+                {
+                    const EstPair w = trips[q];
+                    const uint32_t e0 = estimate_texel<M7, PERC, N>(P, L.at((int) w.i0), axb, pal, thr);
+                    const uint32_t e1 = estimate_texel<M7, PERC, N>(P, L.at((int) w.i1), axb, pal, thr);
+                    sum += e0 + ((w.i0 != w.i1) ? e1 : 0u);
+                }
+            }
+            else
+            {
+#pragma unroll 1
+                for(int k = k0; k < k1; k += 2)
+                {
+                    const bool two = (k + 1 < k1);
+                    const Texel t0 = L.at(order[k]), t1 = L.at(order[two ? k + 1 : k]);
+                    const uint32_t e0 = estimate_texel<M7, PERC, N>(P, t0, axb, pal, thr);
+                    const uint32_t e1 = estimate_texel<M7, PERC, N>(P, t1, axb, pal, thr);
+                    sum += e0 + (two ? e1 : 0u);
+                }
             }
             total += sum;
         }
@@ -1193,7 +1312,7 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
             if(!warp_any(running)) { break; }
             continue;
         }
-        const uint64_t err = estimate_pair<M7, PERC, KEY28, STRIDE>(T, P, L, part);
+        const uint64_t err = estimate_pair<M7, PERC, KEY28, true, STRIDE>(T, P, L, part);
         // bc7enc.cpp:1817-1820 with m_low_frequency_partition_weight == 1.0f (the only value the C ABI accepts) is the identity
         if(need)
         {
@@ -1220,7 +1339,7 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
                 const uint32_t it = base + lane;
                 if(it < total_partitions)
                 {
-                    const uint64_t err = estimate_pair<M7, PERC, KEY28, STRIDE>(T, P, Ls, VKT_UTAB(order)[it]);
+                    const uint64_t err = estimate_pair<M7, PERC, KEY28, false, STRIDE>(T, P, Ls, VKT_UTAB(order)[it]);
                     const uint64_t k = (err << 6) | (uint64_t) it;// err < 2^36: no overflow
                     best_key = k < best_key ? k : best_key;
                 }
@@ -1352,7 +1471,7 @@ VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[
 // mode 1 (bc7enc.cpp:2336-2397) / mode 7 (bc7enc.cpp:2193-2259): estimate, fit both subsets, arbitrate.
 // Called by the whole converged warp; lanes with want == false only help the estimator.
 // Returns the weighted error, or kNoErr when not better than best_err.
-template<int MODE, bool PERC, bool KEY28, int STRIDE>
+template<int MODE, bool PERC, bool KEY28, bool UBER, int STRIDE>
 VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool want, uint64_t best_err, BlockSolution &sol)
 {
     constexpr bool ALPHA = (MODE == 7);
@@ -1371,7 +1490,7 @@ VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, L
     {
         const CellRef cell = {s ? perm1 : perm0, s ? n1 : n0};
         Cell r;
-        trial += compress_cell<MODE, ALPHA, PERC, KEY28, STRIDE>(T, P, L, cell, r);
+        trial += compress_cell<MODE, ALPHA, PERC, KEY28, UBER, STRIDE>(T, P, L, cell, r);
         if(s) { c[1] = r; }
         else { c[0] = r; }
         if(weigh(trial, mw) > best_err) { return kNoErr; }// bc7enc.cpp:2377/2234: cannot be adopted any more
@@ -1500,7 +1619,7 @@ VKT_FN bool block_has_alpha(const Bc7KernelParams &P, const uint32_t px[16])
 // ALPHA == true is handle_alpha_block (:2139-2291).  The caller classifies blocks first so that a warp only ever holds
 // blocks of one kind; the whole warp must call this converged (estimate_partition is warp-cooperative).
 // L: the lane column with texels [0,16) filled; the YCbCr part is filled here.
-template<bool PERC, bool KEY28, bool ALPHA, int STRIDE>
+template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int STRIDE>
 VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
 {
     if(PERC) { prepare_lane<STRIDE>(L); }
@@ -1515,7 +1634,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     if(P.mode_mask & (1u << 6))
     {
         Cell c6;
-        best_err = weigh(compress_cell<6, ALPHA, PERC, KEY28, STRIDE>(T, P, L, whole, c6), P.mode6_w);
+        best_err = weigh(compress_cell<6, ALPHA, PERC, KEY28, UBER, STRIDE>(T, P, L, whole, c6), P.mode6_w);
         sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
     }
     if(!ALPHA)
@@ -1523,7 +1642,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if((P.max_partitions > 0) && (P.mode_mask & (1u << 1)))// warp-uniform condition
         {
             BlockSolution s1 = sol;
-            if(two_subset_trial<1, PERC, KEY28, STRIDE>(T, P, L, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
+            if(two_subset_trial<1, PERC, KEY28, UBER, STRIDE>(T, P, L, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
         }
     }
     else
@@ -1537,7 +1656,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
                 min_a = umin(min_a, a), max_a = umax(max_a, a);
             }
             Cell c5;
-            uint64_t e5 = compress_cell<5, false, PERC, KEY28, STRIDE>(T, P, L, whole, c5);
+            uint64_t e5 = compress_cell<5, false, PERC, KEY28, UBER, STRIDE>(T, P, L, whole, c5);
             uint32_t alo = 0, ahi = 0;
             uint64_t asel = 0;
             e5 += mode5_alpha<STRIDE>(T, P, L, min_a, max_a, alo, ahi, asel);
@@ -1555,7 +1674,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if(P.mode_mask & (1u << 7))// warp-uniform condition
         {
             BlockSolution s7 = sol;
-            if(two_subset_trial<7, PERC, KEY28, STRIDE>(T, P, L, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
+            if(two_subset_trial<7, PERC, KEY28, UBER, STRIDE>(T, P, L, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
         }
     }
     pack_block(T, sol, out);

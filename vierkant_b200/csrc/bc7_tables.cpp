@@ -7,6 +7,7 @@
 #include "bc7_tables.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace vkt
@@ -75,6 +76,23 @@ inline float midpoint(uint32_t i, uint32_t p, uint32_t bins, uint32_t bits, bool
     return (lo + hi) / 2.0f;
 }
 }// namespace
+
+uint64_t bc7_uber_map_reference(int max_sel, int ly, int hy)
+{
+    uint64_t map = 0;
+    for(int sel = 0; sel <= max_sel; ++sel)
+    {
+        // (int)clampf(floorf((float)max_selector * ((float)sel - (float)ly) / ((float)hy - (float)ly) + .5f), 0, (float)max_selector)
+        volatile float num = static_cast<float>(max_sel) * (static_cast<float>(sel) - static_cast<float>(ly));
+        volatile float den = static_cast<float>(hy) - static_cast<float>(ly);
+        volatile float q = num / den;
+        volatile float r = q + .5f;
+        float v = std::floor(r);
+        v = v < 0.0f ? 0.0f : (v > static_cast<float>(max_sel) ? static_cast<float>(max_sel) : v);
+        map |= static_cast<uint64_t>(static_cast<int>(v)) << (4 * sel);
+    }
+    return map;
+}
 
 void bc7_tables_build(Bc7Tables *t)
 {

@@ -39,5 +39,8 @@ static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");
 
 // Filled on the host (product code, C++): vierkant_b200/csrc/bc7_tables.cpp
 void bc7_tables_build(Bc7Tables *t);
+// The reference's float expression for the uber-level selector rescaling (bc7enc.cpp:1399), for checking the
+// integer-generated table in bc7_core.cuh: nibble s of the result is the rescaled selector.
+uint64_t bc7_uber_map_reference(int max_sel, int ly, int hy);
 
 }// namespace vkt

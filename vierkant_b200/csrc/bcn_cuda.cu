@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256) bc7_classify_kernel(const __grid_constant
 }
 
 // One lane == one block of the work list (list == nullptr: every block of the launch, in order).
-template<bool PERC, bool KEY28, bool ALPHA, int NT>
+// UBER == false: the search without the uber-level stages (launched when uber_level == 0).
+template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int NT>
 __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm)
         bc7_encode_kernel(const __grid_constant__ Bc7Batch B, const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables,
                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ count)
@@ -179,28 +180,34 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm
     load_block_texels<NT>(I.img, I.comps, I.stride, I.vec16 != 0, b % I.blocks_x, b / I.blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, KEY28, ALPHA, NT>(s_tables, P, lane, blk);
+    encode_block<PERC, KEY28, ALPHA, UBER, NT>(s_tables, P, lane, blk);
     if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
 constexpr size_t kBc7SmemBytes = sizeof(Bc7Tables) + size_t(kBc7Threads) * 16 * sizeof(Texel);
 
-template<bool PERC, bool KEY28, bool ALPHA>
+template<bool PERC, bool KEY28, bool ALPHA, bool UBER>
 static cudaError_t bc7_kernel_attribute()
 {
-    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
+    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
 }
 // > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
 static cudaError_t bc7_kernel_attributes()
 {
-    cudaError_t e = bc7_kernel_attribute<true, true, false>();
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, false>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, true>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, false>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, true>(); }
+    cudaError_t e = bc7_kernel_attribute<true, true, false, false>();
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true, false>(); }
+#ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, true, true>(); }
+#endif
     return e;
 }
 
@@ -375,17 +382,26 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
         const uint32_t grid = (B.total_blocks + kBc7Threads - 1) / kBc7Threads;
         auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
             auto go = [&](auto kernel) { kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(B, kp, s->d_tables, list, cnt); };
-            const int sel = (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            // uber-free kernels exist for the 28-bit-key variants (every sane weight set); the wide-error ones always carry the stages
+            const int sel = ((kp.uber_level == 0 && kp.key28) ? 8 : 0) | (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
             switch(sel)
             {
-                case 7: go(bc7_encode_kernel<true, true, true, kBc7Threads>); break;
-                case 6: go(bc7_encode_kernel<true, true, false, kBc7Threads>); break;
-                case 5: go(bc7_encode_kernel<true, false, true, kBc7Threads>); break;
-                case 4: go(bc7_encode_kernel<true, false, false, kBc7Threads>); break;
-                case 3: go(bc7_encode_kernel<false, true, true, kBc7Threads>); break;
-                case 2: go(bc7_encode_kernel<false, true, false, kBc7Threads>); break;
-                case 1: go(bc7_encode_kernel<false, false, true, kBc7Threads>); break;
-                default: go(bc7_encode_kernel<false, false, false, kBc7Threads>); break;
+                case 15: go(bc7_encode_kernel<true, true, true, false, kBc7Threads>); break;
+                case 14: go(bc7_encode_kernel<true, true, false, false, kBc7Threads>); break;
+#ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY// (tuning builds compile the two default-parameter kernels only)
+                case 11: go(bc7_encode_kernel<false, true, true, false, kBc7Threads>); break;
+                case 10: go(bc7_encode_kernel<false, true, false, false, kBc7Threads>); break;
+                case 7: go(bc7_encode_kernel<true, true, true, true, kBc7Threads>); break;
+                case 6: go(bc7_encode_kernel<true, true, false, true, kBc7Threads>); break;
+                case 5: go(bc7_encode_kernel<true, false, true, true, kBc7Threads>); break;
+                case 4: go(bc7_encode_kernel<true, false, false, true, kBc7Threads>); break;
+                case 3: go(bc7_encode_kernel<false, true, true, true, kBc7Threads>); break;
+                case 2: go(bc7_encode_kernel<false, true, false, true, kBc7Threads>); break;
+                case 1: go(bc7_encode_kernel<false, false, true, true, kBc7Threads>); break;
+                default: go(bc7_encode_kernel<false, false, false, true, kBc7Threads>); break;
+#else
+                default: break;
+#endif
             }
         };
         if(kp.force_alpha)
@@ -473,6 +489,26 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
     if(!ctx) { return VKT_BCN_ERR_OOM; }
     Bc7Tables host_tables;
     bc7_tables_build(&host_tables);
+    {
+        // the compile-time uber-level selector maps (bc7_core.cuh) against the reference's float expression
+        const UberMaps um = make_uber_maps();
+        for(int k = 0; k < 3; ++k)
+        {
+            const int max_sel = (k == 0) ? 3 : (k == 1) ? 7 : 15;
+            const uint64_t live = (max_sel == 15) ? ~0ull : ((1ull << (4 * (max_sel + 1))) - 1ull);
+            for(int ly = -2; ly <= 1; ++ly)
+            {
+                for(int hy = max_sel - 1; hy <= max_sel + 2; ++hy)
+                {
+                    if((um.m[k][ly + 2][hy - (max_sel - 1)] & live) != (bc7_uber_map_reference(max_sel, ly, hy) & live))
+                    {
+                        vkt_bcn_cuda_destroy(ctx);
+                        return fail(nullptr, VKT_BCN_ERR_INVALID, "internal: uber selector map mismatch (max %d, ly %d, hy %d)", max_sel, ly, hy);
+                    }
+                }
+            }
+        }
+    }
     for(int i = 0; i < num_devices; ++i)
     {
         const int dev = devices ? devices[i] : i;
