@@ -33,4 +33,6 @@ with capi.BcnContext([0]) as ctx:
         ev[i + 1].record()
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.launches)]
-    print("kernel ms:", ["%.3f" % m for m in ms], "Mpix/s: %.1f" % (a.size * a.size / min(ms) * 1e-3))
+    import hashlib
+    digest = hashlib.sha1(d_out.cpu().numpy().tobytes()).hexdigest()[:12]
+    print("kernel ms:", ["%.3f" % m for m in ms], "Mpix/s: %.1f" % (a.size * a.size / min(ms) * 1e-3), "sha1", digest)

@@ -77,9 +77,11 @@ constexpr EstLists make_est_lists()
 }
 // The same lists as texel PAIRS, the unit of the estimator's loops: pairs [0, n[p] & 255) walk subset 0, pairs
 // [n[p] & 255, n[p] >> 8) subset 1; an odd subset ends with a pair that names its last texel twice (i0 == i1).
-struct EstPair
+struct alignas(16) EstPair
 {
     uint32_t i0, i1;
+    uint32_t second;// all ones if i1 is a texel of its own, 0 if it repeats i0 (its error must not be counted again)
+    uint32_t pad;
 };
 struct EstTrips
 {
@@ -94,9 +96,17 @@ constexpr EstTrips make_est_trips()
     {
         int m = 0;
         const int n0 = (int) l.n0[p];
-        for(int k = 0; k < n0; k += 2) { t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < n0) ? k + 1 : k], ++m; }
+        for(int k = 0; k < n0; k += 2)
+        {
+            t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < n0) ? k + 1 : k], t.t[p][m].second = (k + 1 < n0) ? 0xFFFFFFFFu : 0u;
+            ++m;
+        }
         const int m0 = m;
-        for(int k = n0; k < 16; k += 2) { t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < 16) ? k + 1 : k], ++m; }
+        for(int k = n0; k < 16; k += 2)
+        {
+            t.t[p][m].i0 = l.idx[p][k], t.t[p][m].i1 = l.idx[p][(k + 1 < 16) ? k + 1 : k], t.t[p][m].second = (k + 1 < 16) ? 0xFFFFFFFFu : 0u;
+            ++m;
+        }
         t.n[p] = (uint32_t) m0 | ((uint32_t) m << 8);
     }
     return t;
@@ -272,6 +282,8 @@ struct Bc7KernelParams
     uint32_t force_alpha;
     uint32_t bias_mode1_pbits;
     uint32_t key28;// 1 if every per-texel error is provably < 2^28 for these weights (packed argmin keys are then exact)
+    uint32_t w16[4];// w * 16, for those keys: prepared on the host so the selector search multiplies by them directly (the
+                    // compiler otherwise multiplies by w and shifts every key)
     float pbit1_weight;
     float mode1_w, mode5_w, mode6_w, mode7_w;
 };
@@ -504,7 +516,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
         if(KEY28)
         {
             // error < 2^28 for every texel (checked on the host from the weights): key = err * 16 + j, one min per candidate.
-            const uint32_t w0 = P.w[0] * 16u, w1 = P.w[1] * 16u, w2 = P.w[2] * 16u, w3 = P.w[3] * 16u;
+            const uint32_t w0 = P.w16[0], w1 = P.w16[1], w2 = P.w16[2], w3 = P.w16[3];
             for(int k = 0; k < cell.n; ++k)
             {
                 const int i = cell.at(k);
@@ -1145,7 +1157,11 @@ VKT_FN uint32_t estimate_texel(const Bc7KernelParams &P, const Texel t, uint32_t
     uint32_t e;
     if(PERC)
     {
-        const Ycc e1 = to_ycc_packed(c);
+        // mode 1 palettes carry g again in the (unused) alpha byte: luma is then a single dot product, 183 g + 183 g = 366 g
+        Ycc e1;
+        e1.l = M7 ? (int) dp4a_u8(c, 0x0025B76Du, dp4a_u8(c, 0x0000B700u, 0u)) : (int) dp4a_u8(c, 0xB725B76Du, 0u);
+        e1.cr = (int) (byte_of(c, 0) << 9) - e1.l;
+        e1.cb = (int) (byte_of(c, 2) << 9) - e1.l;
         const int dl = (e1.l - t.l) >> 8, dcr = (e1.cr - t.cr) >> 8, dcb = (e1.cb - t.cb) >> 8;
         // uint32 products, bc7enc.cpp:1533,1670
         e = (P.w[0] * (uint32_t) dl * (uint32_t) dl) + (P.w[1] * (uint32_t) dcr * (uint32_t) dcr) + (P.w[2] * (uint32_t) dcb * (uint32_t) dcb);
@@ -1207,9 +1223,10 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             for(int k = k0; k < k1; k += 2) { grow(L.px(order[k]), L.px(order[(k + 1 < k1) ? k + 1 : k])); }
         }
         // palette: lo*(64-w) + hi*w + 32 = 64*lo + (hi-lo)*w + 32 per 16-bit lane (<= 16352: no carries between lanes)
+        // -- computed four-fold, see below
         const uint32_t ax_rg = h_rg - l_rg, ax_ba = h_ba - l_ba;// hi >= lo per lane (subsets are never empty)
-        const uint32_t axb = prmt(ax_rg, ax_ba, 0x6420u);      // (ar, ag, ab, aa) as bytes
-        const uint32_t c_rg = l_rg * 64u + 0x00200020u, c_ba = l_ba * 64u + 0x00200020u;
+        const uint32_t axb = prmt(ax_rg, ax_ba, M7 ? 0x6420u : 0x1420u);// (ar, ag, ab, aa) as bytes; mode 1: (ar, ag, ab, 0)
+        const uint32_t c4_rg = l_rg * 256u + 0x00800080u, c4_ba = l_ba * 256u + 0x00800080u;
         uint32_t pal[N];
         int thr[N - 1];
         {
@@ -1217,13 +1234,15 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
 #pragma unroll
             for(int j = 0; j < N; ++j)
             {
-                if(j == 0) { pal[j] = prmt(l_rg, l_ba, 0x6420u); }
-                else if(j == N - 1) { pal[j] = prmt(h_rg, h_ba, 0x6420u); }
+                // packed (r, g, b, a) for mode 7, (r, g, b, g) for mode 1 (estimate_texel's single-dot luma)
+                if(j == 0) { pal[j] = prmt(l_rg, l_ba, M7 ? 0x6420u : 0x2420u); }
+                else if(j == N - 1) { pal[j] = prmt(h_rg, h_ba, M7 ? 0x6420u : 0x2420u); }
                 else
                 {
                     const uint32_t w = (uint32_t) selw(N, j);
-                    // bytes 0 and 2 of each shifted word hold the two interpolated channels; PRMT gathers them
-                    pal[j] = prmt((ax_rg * w + c_rg) >> 6, (ax_ba * w + c_ba) >> 6, 0x6420u);
+                    // 4 * (lo*64 + (hi-lo)*w + 32) <= 65408 still fits the 16-bit lane: the interpolated channel is then byte 1 / 3
+                    // of each word and PRMT gathers it without a shift
+                    pal[j] = prmt(ax_rg * (4u * w) + c4_rg, ax_ba * (4u * w) + c4_ba, M7 ? 0x7531u : 0x3531u);
                 }
                 dots[j] = (int) dp4a_u8(pal[j], axb, 0u);
             }
@@ -1242,7 +1261,7 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
                     const EstPair w = trips[q];
                     const uint32_t e0 = estimate_texel<M7, PERC, N>(P, L.at((int) w.i0), axb, pal, thr);
                     const uint32_t e1 = estimate_texel<M7, PERC, N>(P, L.at((int) w.i1), axb, pal, thr);
-                    sum += e0 + ((w.i0 != w.i1) ? e1 : 0u);
+                    sum += e0 + (e1 & w.second);
                 }
             }
             else

@@ -62,6 +62,7 @@ inline int bc7_prepare_params(const vkt_bc7_params *p, Bc7KernelParams *k)
                                          : ((uint64_t) k->w[0] + k->w[1] + k->w[2] + k->w[3]) * 255 * 255;
         k->key28 = (b < (1ull << 28)) ? 1u : 0u;
     }
+    for(int i = 0; i < 4; ++i) { k->w16[i] = k->w[i] * 16u; }// only read when key28 (then w * 16 * d^2 < 2^32)
     k->uber_level = p->uber_level;
     k->try_least_squares = p->try_least_squares != 0;
     k->filterbank = p->mode17_partition_estimation_filterbank != 0;
