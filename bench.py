@@ -55,6 +55,10 @@ WORKLOADS = {
                ops_per_pixel=3.3e3,
                name="8192x8192 RGBA8 with alpha gradients (synthetic kind 1: modes 1/5/6/7) + full mip chain, max partitions",
                params_name="perceptual, 64 partitions, filterbank off (every pattern is a candidate), uber 0"),
+    "c4": dict(base=4096, kind=0, rotate=1, textures=8, params=dict(), ops_per_pixel=2.9e3,
+               name="glTF-like material batch: 8 x 4096x4096 RGBA8 textures + mips per GPU (64 over 8 GPUs), every 4th with alpha "
+                    "(synthetic kind 1), all encoded as BC7",
+               params_name="bc7enc defaults (perceptual, 64 partitions, filterbank on, uber 0)"),
     "c5": dict(base=16384, kind=0, rotate=1,
                params=dict(uber_level=4, max_partitions=64, mode17_partition_estimation_filterbank=0), ops_per_pixel=1.3e4,
                name="16384x16384 RGBA8 opaque (synthetic kind 0) + full mip chain, highest quality",
@@ -259,31 +263,40 @@ def main():
     wl = WORKLOADS[args.workload]
     base = args.base or wl["base"]
     KIND, ROTATE, OPS_PER_PIXEL = wl["kind"], wl["rotate"], wl["ops_per_pixel"]
+    NTEX = wl.get("textures", 1)  # textures per GPU and step (c4: a material batch, encoded one compress() call each)
     WORKLOAD = wl["name"] if base == wl["base"] else wl["name"].replace(f"{wl['base']}x{wl['base']}", f"{base}x{base}")
     ctx = capi.BcnContext([local])
     params = capi.default_params(**wl["params"])
     dims = chain_dims(base)
-    npix = sum(w * h for w, h in dims)
-    nblocks = sum((w // 4) * (h // 4) for w, h in dims)
+    npix = sum(w * h for w, h in dims) * NTEX
+    nblocks = sum((w // 4) * (h // 4) for w, h in dims) * NTEX
 
     # synthetic level images (every level generated at its own size by the App. C generator; per-rank seeds)
     host_levels = []   # [rotation][level] pinned uint8 tensors
     dev_levels = []
-    for r in range(ROTATE):
+    for r in range(ROTATE * NTEX):
         hl, dl = [], []
+        kind = KIND if NTEX == 1 else (1 if (r % 4 == 3) else 0)
         for (w, h) in dims:
-            img = synth.make_texture(w, h, KIND, seed=0xB200 + 16 * rank + r)
+            img = synth.make_texture(w, h, kind, seed=0xB200 + 16 * rank + r)
             t = torch.from_numpy(img).pin_memory()
             hl.append(t)
             dl.append(t.to(dev, non_blocking=True))
         host_levels.append(hl)
         dev_levels.append(dl)
-    dev_out = [torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8, device=dev) for (w, h) in dims]
+    dev_out = [[torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8, device=dev) for (w, h) in dims] for _ in range(NTEX)]
     host_out = [torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8).pin_memory() for (w, h) in dims]
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
 
-    dev_batches = [ctx.make_device_batch([(t, w, h, 4) for t, (w, h) in zip(lv, dims)], dev_out) for lv in dev_levels]
+    # one device batch per rotation: the levels of its NTEX textures
+    dev_batches = []
+    for r in range(ROTATE):
+        ims, outs = [], []
+        for j in range(NTEX):
+            ims += [(t, w, h, 4) for t, (w, h) in zip(dev_levels[r * NTEX + j], dims)]
+            outs += dev_out[j]
+        dev_batches.append(ctx.make_device_batch(ims, outs))
 
     def step_device(i):
         # all 11 levels of the chain in one call: one classify + two encode launches (vkt_bcn_cuda_encode_batch_device)
@@ -293,9 +306,10 @@ def main():
     out_ptrs = (C.c_void_p * len(dims))(*[t.data_ptr() for t in host_out])
 
     def step_e2e(i):
-        src = host_levels[i % ROTATE][0]  # the level-0 texture is the source image of the chain
-        ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
-                                                 C.byref(params), out_ptrs))
+        for j in range(NTEX):  # a material batch is one compress() per texture, as model::compress_textures calls it
+            src = host_levels[(i % ROTATE) * NTEX + j][0]  # the level-0 texture is the source image of the chain
+            ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                     C.byref(params), out_ptrs))
 
     def barrier():
         if world > 1:
@@ -325,10 +339,10 @@ def main():
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kms = []
     for i in range(max(3, min(args.steps, 10))):
-        lv = dev_levels[i % ROTATE]
+        lv = dev_levels[(i % ROTATE) * NTEX]
         torch.cuda.synchronize()
         k0.record()
-        ctx.encode_bc7_device(lv[0], dims[0][0], dims[0][1], 4, dev_out[0], params, 0, stream)
+        ctx.encode_bc7_device(lv[0], dims[0][0], dims[0][1], 4, dev_out[0][0], params, 0, stream)
         k1.record()
         torch.cuda.synchronize()
         kms.append(k0.elapsed_time(k1))
@@ -372,9 +386,9 @@ def main():
             "metric": "bc7_encode_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32+f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "levels": len(dims), "blocks_per_step_per_gpu": nblocks,
-                       "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world} independent texture chains, one per GPU, no collective",
-                       "l2": f"{ROTATE} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
+            "config": {"workload": WORKLOAD, "levels": len(dims), "textures_per_gpu": NTEX, "blocks_per_step_per_gpu": nblocks,
+                       "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world * NTEX} independent texture chains, {NTEX} per GPU, no collective",
+                       "l2": f"{ROTATE * NTEX} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
                        "params": wl["params_name"]},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,

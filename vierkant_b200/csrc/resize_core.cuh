@@ -47,6 +47,11 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
                                                         const int *__restrict__ start, const int *__restrict__ idx,
                                                         const float *__restrict__ coef, float *__restrict__ band)
 {
+    // stbir decodes a sample as u8 / 255.0f (:1252-1291): one correctly rounded division per value, taken from a table of
+    // the 256 quotients instead of being redone per tap and channel (the pass is otherwise bound by those divisions)
+    __shared__ float s_decode[256];
+    s_decode[threadIdx.x] = __fdiv_rn((float) threadIdx.x, 255.0f);
+    __syncthreads();
     const int x = blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
     if(x >= out_w || r >= rows) { return; }
     const uint8_t *row = src + size_t(row0 + r) * size_t(in_w) * C;
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
             for(int c = 0; c < C; ++c) { v[c] = p[c]; }
         }
 #pragma unroll
-        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(__fdiv_rn((float) v[c], 255.0f), w)); }
+        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(s_decode[v[c]], w)); }
     }
     float *o = band + (size_t(r) * size_t(out_w) + size_t(x)) * C;
 #pragma unroll
