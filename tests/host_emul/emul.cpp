@@ -11,6 +11,7 @@
 
 #include "../../vierkant_b200/csrc/bc7_core.cuh"
 #include "../../vierkant_b200/csrc/bc7_params.h"
+#include "../../vierkant_b200/csrc/chain_plan.h"
 #include "../../vierkant_b200/csrc/resize_axis.h"
 
 // the uber-free instantiation whenever the parameters allow it, as the CUDA dispatch does
@@ -22,6 +23,53 @@ static void enc(const vkt::Bc7Tables &tables, const vkt::Bc7KernelParams &kp, vk
 }
 
 extern "C" {
+
+// The multi-device plan of one compress() chain (chain_plan.h) for device g of G, with the real stbir tap ranges.
+// level_height: the chain's level heights (level 0 = rounded base height); src_height: the source image's height.
+// Outputs (per level l < 16): own block rows, needed pixel rows, and for l == 0 the source rows the need range reads.
+// Returns sliced-level count M in the low byte, participating devices in the next byte, or -1 if need[] does not cover
+// the taps of the next level (the property the plan must guarantee).
+int emul_chain_plan(const uint32_t *level_height, uint32_t num_levels, uint32_t src_height, uint32_t G, uint32_t g, uint32_t *own0, uint32_t *own1,
+                    uint32_t *need0, uint32_t *need1, uint32_t *src0, uint32_t *src1)
+{
+    const vkt::ChainSplit split = vkt::chain_split(level_height, num_levels, G);
+    if(g >= split.devices) { return int(split.sliced | (split.devices << 8)); }
+    std::vector<vkt::ResizeAxis> ax(split.sliced);
+    std::vector<std::vector<int>> first(split.sliced), last(split.sliced);
+    std::vector<vkt::RowTaps> taps(split.sliced);
+    for(uint32_t l = 0; l < split.sliced; ++l)
+    {
+        const int in = int(l ? level_height[l - 1] : src_height), out = int(level_height[l]);
+        ax[l].build(in, out);
+        first[l].resize(size_t(out)), last[l].resize(size_t(out));
+        for(int o = 0; o < out; ++o)
+        {
+            int lo = in - 1, hi = 0;
+            for(int t = ax[l].start[size_t(o)]; t < ax[l].start[size_t(o) + 1]; ++t) { lo = std::min(lo, ax[l].idx[size_t(t)]), hi = std::max(hi, ax[l].idx[size_t(t)]); }
+            if(ax[l].start[size_t(o)] == ax[l].start[size_t(o) + 1]) { lo = hi = 0; }
+            first[l][size_t(o)] = lo, last[l][size_t(o)] = hi;
+        }
+        taps[l] = {first[l].data(), last[l].data()};
+    }
+    const vkt::DeviceRows r = vkt::device_rows(split, level_height, taps.data(), g);
+    for(uint32_t l = 0; l < split.sliced; ++l)
+    {
+        own0[l] = r.own[l].first, own1[l] = r.own[l].second, need0[l] = r.need[l].first, need1[l] = r.need[l].second;
+        if(l + 1 < split.sliced)
+        {
+            for(uint32_t y = r.need[l + 1].first; y < r.need[l + 1].second; ++y)
+            {
+                if(uint32_t(first[l + 1][y]) < r.need[l].first || uint32_t(last[l + 1][y]) >= r.need[l].second) { return -1; }
+            }
+        }
+    }
+    if(split.sliced)
+    {
+        const auto s = vkt::source_rows(taps[0], r.need[0].first, r.need[0].second, src_height);
+        *src0 = s.first, *src1 = s.second;
+    }
+    return int(split.sliced | (split.devices << 8));
+}
 
 // number of (max, ly, hy) cells whose compile-time uber selector map differs from the reference's float expression
 int emul_uber_map_mismatches()

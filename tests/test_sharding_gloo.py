@@ -13,13 +13,60 @@ from vierkant_b200 import sharding, synth
 @pytest.mark.parametrize("w,h,world", [(4096, 4096, 8), (1024, 512, 2), (124, 84, 4), (4, 4, 8), (16384, 16384, 8), (260, 12, 3)])
 def test_plan_covers_every_block_once(w, h, world):
     dims = sharding.chain_dims(w, h)
+    plans = [sharding.shard_plan(w, h, r, world) for r in range(world)]
     for l, (lw, lh) in enumerate(dims):
         rows = lh // 4
         seen = np.zeros(rows, dtype=np.int32)
         for r in range(world):
-            r0, r1 = sharding.level_rows(l, rows, r, world)
+            r0, r1 = plans[r][l]["rows"]
             seen[r0:r1] += 1
         assert (seen == 1).all(), (l, lw, lh)
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-s", "-C", os.path.join(here, "host_emul")], check=True)
+    lib = C.CDLL(os.path.join(here, "host_emul", "libvkt_emul.so"))
+    u32p = C.POINTER(C.c_uint32)
+    lib.emul_chain_plan.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p, u32p, u32p, u32p]
+    return lib
+
+
+@pytest.mark.parametrize("w,h,world", [(4096, 4096, 8), (4096, 4096, 2), (8192, 8192, 8), (1000, 520, 2), (2050, 2046, 4), (1024, 4096, 3),
+                                        (16384, 16384, 8), (512, 512, 2), (260, 12, 3), (123, 81, 2), (2048, 2048, 5)])
+def test_multi_device_chain_plan(emul_lib, w, h, world):
+    """The C++ plan compress() uses on several devices (chain_plan.h, with the real stbir tap ranges): the Python mirror
+    agrees on the split; own rows partition every sliced level; the rows a device produces at level l cover every tap
+    of the rows it produces at level l + 1; the source rows it uploads shrink towards 1 / G of the image."""
+    import ctypes as C
+    dims = sharding.chain_dims(w, h)
+    heights = (C.c_uint32 * len(dims))(*[lh for _, lh in dims])
+    m_py, workers_py = sharding.chain_split([lh for _, lh in dims], world)
+    covered = [np.zeros(lh // 4, dtype=np.int32) for _, lh in dims]
+    uploads = []
+    for g in range(world):
+        arr = [(C.c_uint32 * 16)() for _ in range(4)]
+        s0, s1 = C.c_uint32(), C.c_uint32()
+        rc = emul_lib.emul_chain_plan(heights, len(dims), h, world, g, arr[0], arr[1], arr[2], arr[3], C.byref(s0), C.byref(s1))
+        assert rc >= 0, "need[] does not cover the taps of the next level"
+        m, workers = rc & 255, rc >> 8
+        assert (m, workers) == (m_py, workers_py)
+        if g >= workers:
+            continue
+        py = sharding.shard_plan(w, h, g, world)
+        for l in range(m):
+            own, need = (arr[0][l], arr[1][l]), (arr[2][l], arr[3][l])
+            assert py[l]["rows"] == own
+            assert need[0] <= own[0] * 4 and need[1] >= own[1] * 4 and need[1] <= dims[l][1]
+            covered[l][own[0]:own[1]] += 1
+        uploads.append(s1.value - s0.value)
+    for l in range(m_py):
+        assert (covered[l] == 1).all()
+    if workers_py > 1:
+        assert max(uploads) <= h / workers_py * 1.45 + 16  # own slice + halo, not the whole image
 
 
 def test_chain_dims_match_the_reference_formula():
@@ -38,10 +85,10 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         oracle = pyoracle.PortOracle()
-        img = synth.make_texture(128, 64, 1, seed=5)
+        img = synth.make_texture(256, 512, 1, seed=5)  # levels 512 and 256 rows are split over the 2 workers, the rest is worker 0's
         # every worker derives the level images itself (the cheap part), encodes only its rows of every level
         pieces, prev = [], img
-        for p in sharding.shard_plan(128, 64, rank, world):
+        for p in sharding.shard_plan(256, 512, rank, world):
             prev = oracle.resize(prev, p["width"], p["height"])
             r0, r1 = p["rows"]
             if r1 > r0:

@@ -658,8 +658,9 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
                     }
                     else
                     {
-                        ql = clampi(f2i(fadd(fdiv(fsub(fmul(xl[c], scalep), (float) p), 2.0f), .5f)) * 2 + p, p, iscalep - 1 + p);
-                        qh = clampi(f2i(fadd(fdiv(fsub(fmul(xh[c], scalep), (float) p), 2.0f), .5f)) * 2 + p, p, iscalep - 1 + p);
+                        // (x * scalep - p) / 2.0f: halving is exact, so the multiply by .5f is the same correctly rounded value
+                        ql = clampi(f2i(fadd(fmul(fsub(fmul(xl[c], scalep), (float) p), .5f), .5f)) * 2 + p, p, iscalep - 1 + p);
+                        qh = clampi(f2i(fadd(fmul(fsub(fmul(xh[c], scalep), (float) p), .5f), .5f)) * 2 + p, p, iscalep - 1 + p);
                     }
                     qlo |= (uint32_t) ql << (8 * c);
                     qhi |= (uint32_t) qh << (8 * c);
@@ -739,8 +740,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
 #pragma unroll
                 for(int c = 0; c < NCOMP; ++c)
                 {
-                    e = fadd(e, fadd(sqf(fsub(fdiv((float) byte_of(slo, c), 255.0f), xl[c])),
-                                     sqf(fsub(fdiv((float) byte_of(shi, c), 255.0f), xh[c]))));
+                    e = fadd(e, fadd(sqf(fsub(T.unit8[byte_of(slo, c)], xl[c])), sqf(fsub(T.unit8[byte_of(shi, c)], xh[c]))));// s / 255.0f
                 }
                 if(p == 1) { e = fmul(e, P.pbit1_weight); }
                 if(e < beste)

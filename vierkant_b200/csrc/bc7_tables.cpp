@@ -121,6 +121,7 @@ void bc7_tables_build(Bc7Tables *t)
         }
     }
 
+    for(uint32_t v = 0; v < 256; ++v) { t->unit8[v] = static_cast<float>(v) / 255.0f; }
     for(uint32_t p = 0; p < 2; ++p)
     {
         for(uint32_t i = 0; i < 32; ++i) { t->mid7[i][p] = midpoint(i, p, 32, 6, true); }

@@ -33,6 +33,7 @@ struct Bc7Tables
     uint64_t est_perm[64];// the same list, one nibble per texel
     uint8_t est_idx[64][16];
     uint8_t est_n0[64];
+    float unit8[256];// v / 255.0f, the correctly rounded quotient find_optimal_solution divides out per component (bc7enc.cpp:1040-1042)
 };
 
 static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");

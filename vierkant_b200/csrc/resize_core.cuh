@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 
+#include "chain_plan.h"
 #include "resize_axis.h"
 
 namespace vkt
@@ -300,18 +301,9 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             if(e > prev) { out.push_back({prev * 4, e * 4, true}), prev = e; }
         }
     };
-    // Several devices: levels [0, M) are "sliced" -- every device resizes and encodes its own block rows of each, from
-    // just the source rows those reach through the filter taps (own rows plus a halo that grows by ~5 rows per level).
-    // Slicing stops where the halo would outgrow the slice (level height < 128 rows per device): the small levels
-    // [M, L) are all done by device 0, from level M-1 gathered through a pinned host buffer (<= a few hundred KB).
-    const uint32_t L = plan.num_levels;
-    uint32_t M = L, Geff = G;
-    if(G > 1)
-    {
-        M = 0;
-        while(M < L && plan.level_height[M] / 4 >= G * 4 && plan.level_height[M] >= 128u * G) { ++M; }
-        if(M == 0) { Geff = 1, M = L; }// too small to slice: device 0 does the whole chain
-    }
+    // Several devices: levels [0, M) are sliced by block rows, the small levels [M, L) finished by device 0 (chain_plan.h)
+    const ChainSplit split = chain_split(plan.level_height, plan.num_levels, G);
+    const uint32_t L = split.levels, M = split.sliced, Geff = split.devices;
     const bool tail = M < L;
     DeviceSlot *ev_slot = nullptr;// events come from the current slot's pool (created once per context, reused by every call)
     // VKT_BCN_TRACE=1: events carry timestamps and the call prints its device timeline to stderr (diagnostics only)
@@ -363,26 +355,10 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         if(rc) { break; }
         // own[l]: this device's block rows of level l;  need[l]: the pixel rows of level l it has to produce (own rows
         // plus whatever its rows of level l+1 read)
-        std::vector<std::pair<uint32_t, uint32_t>> own(M), need(M);
-        for(uint32_t l = 0; l < M; ++l)
-        {
-            const uint32_t rows = plan.level_height[l] / 4;
-            own[l] = {uint32_t(uint64_t(rows) * g / Geff), uint32_t(uint64_t(rows) * (g + 1) / Geff)};
-        }
-        for(uint32_t l = M; l-- > 0;)
-        {
-            need[l] = {own[l].first * 4, own[l].second * 4};
-            if(l + 1 < M)
-            {
-                uint32_t lo = need[l].first, hi = need[l].second;
-                for(uint32_t y = need[l + 1].first; y < need[l + 1].second; ++y)
-                {
-                    lo = std::min(lo, uint32_t(ay[l + 1]->first_in[y])), hi = std::max(hi, uint32_t(ay[l + 1]->last_in[y]) + 1u);
-                }
-                need[l] = {lo, std::min(hi, plan.level_height[l])};
-            }
-        }
-        const DeviceAxis *ay0 = ay[0];
+        std::vector<RowTaps> taps(M);
+        for(uint32_t l = 0; l < M; ++l) { taps[l] = {ay[l]->first_in.data(), ay[l]->last_in.data()}; }
+        const DeviceRows dr = device_rows(split, plan.level_height, taps.data(), g);
+        const std::vector<std::pair<uint32_t, uint32_t>> &own = dr.own, &need = dr.need;
         // This device's bands of level 0, in processing order: its own block rows first (graded, encoded), then the halo
         // rows above and below (resized only).  Source rows are uploaded in the same order, each band fetching just the
         // rows its resize taps reach that are not on the device yet.
@@ -399,9 +375,8 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         auto upload = [&](uint32_t k) -> int {
             if(queued[k]) { return VKT_BCN_OK; }
             queued[k] = 1;
-            uint32_t lo = height, hi = 0;
-            for(uint32_t y = bands[k].y0; y < bands[k].y1; ++y) { lo = std::min(lo, uint32_t(ay0->first_in[y])), hi = std::max(hi, uint32_t(ay0->last_in[y]) + 1u); }
-            hi = std::min(hi, height);
+            const std::pair<uint32_t, uint32_t> rows = source_rows(taps[0], bands[k].y0, bands[k].y1, height);
+            const uint32_t lo = rows.first, hi = rows.second;
             // subtract what is already there
             std::vector<std::pair<uint32_t, uint32_t>> todo;
             if(lo < hi) { todo.push_back({lo, hi}); }
