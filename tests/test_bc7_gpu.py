@@ -143,3 +143,57 @@ def test_full_size_properties_4096(ctx, port_oracle):
     dec = port_oracle.unpack_blocks(full[idx]).astype(np.float64)
     mse = ((dec - tiles.astype(np.float64)) ** 2).mean()
     assert 10 * np.log10(255 ** 2 / mse) > 30.0
+
+
+@pytest.mark.parametrize("name,size,kind,kw,sample", [
+    ("c3", 8192, 1, dict(max_partitions=64, mode17_partition_estimation_filterbank=0), 12000),
+    ("c5", 2048, 0, dict(uber_level=4, max_partitions=64, mode17_partition_estimation_filterbank=0), 4000),
+])
+def test_full_size_properties_other_configs(ctx, port_oracle, name, size, kind, kw, sample):
+    """BASELINE configs[2] (8192^2, alpha, every partition a candidate) at full size and the parameter set of configs[4]
+    (uber 4) on a 2048^2 level: crops encode like the whole, a random sample of blocks matches the oracle, repeatable."""
+    img = synth.make_texture(size, size, kind)
+    full = ctx.encode_bc7(img, gpu_params(kw))
+    bx = size // 4
+    y0, x0 = size // 2 - 128, size // 2 - 256  # straddles the opaque / alpha halves of kind 1
+    crop = np.ascontiguousarray(img[y0:y0 + 256, x0:x0 + 512])
+    rows = (np.arange(256 // 4) + y0 // 4)[:, None] * bx + (np.arange(512 // 4) + x0 // 4)[None, :]
+    assert np.array_equal(ctx.encode_bc7(crop, gpu_params(kw)), full[rows.ravel()])
+    rng = np.random.default_rng(11)
+    idx = rng.choice(full.shape[0], sample, replace=False)
+    # tiles of the sampled blocks without materialising every tile of the image
+    by, bxs = idx // bx, idx % bx
+    tiles = np.stack([img[4 * y:4 * y + 4, 4 * x:4 * x + 4].reshape(16, 4) for y, x in zip(by, bxs)])
+    assert np.array_equal(full[idx], port_oracle.encode_blocks(tiles, oracle_params(**kw), threads=os.cpu_count() or 1))
+    if kind == 1:
+        modes = synth.mode_histogram(full)
+        assert set(modes) == {1, 5, 6, 7}  # the alpha half exercises every alpha mode
+
+
+def test_concurrent_calls_on_one_context(ctx, port_oracle):
+    """vierkant's loader may call compress() from several host threads (SURVEY.md 8b "Threading"): one context, four
+    threads, mixed entry points; every result must be the single-threaded one."""
+    import threading
+    imgs = [synth.make_texture(256, 128, i & 1, seed=40 + i) for i in range(4)]
+    want_blocks = [ctx.encode_bc7(im) for im in imgs]
+    want_chain = [ctx.compress(im, capi.MODE_BC7, True)[1] for im in imgs]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(6):
+                if not np.array_equal(ctx.encode_bc7(imgs[i]), want_blocks[i]):
+                    errors.append(("blocks", i))
+                _, lv = ctx.compress(imgs[i], capi.MODE_BC7, True)
+                if not all(np.array_equal(a, b) for a, b in zip(lv, want_chain[i])):
+                    errors.append(("chain", i))
+        except Exception as e:  # noqa: BLE001
+            errors.append((repr(e), i))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    assert np.array_equal(want_blocks[1], port_oracle.encode_blocks(synth.to_blocks(imgs[1])))
