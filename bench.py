@@ -141,6 +141,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(local: int):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs NVML reports as local to
+    its GPU: with one process per GPU the H2D / D2H streams then stay on the GPU's own NUMA node instead of crossing the
+    socket interconnect.  Returns a short description for the JSON line; never fatal."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} CPUs local to the GPU ({allowed[0]}..{allowed[-1]})"
+        return "no local CPU set reported"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def cpu_baseline_sample(threads: int | None = None, reps: int = 2):
     """The reference's CPU path on a bounded sample: vierkant::bcn::compress() of the top-left 2048x2048 crop of the
     workload texture with mipmaps, delegate = thread pool with all host threads (as model::compress_textures does).
@@ -244,6 +269,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path")
     torch.cuda.set_device(local)
+    affinity = bind_near_gpu(local) if world > 1 else "single process: not bound"
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL announces its version on stdout when the first communicator is made: keep stdout for the one JSON line
@@ -389,7 +415,7 @@ def main():
             "config": {"workload": WORKLOAD, "levels": len(dims), "textures_per_gpu": NTEX, "blocks_per_step_per_gpu": nblocks,
                        "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world * NTEX} independent texture chains, {NTEX} per GPU, no collective",
                        "l2": f"{ROTATE * NTEX} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
-                       "params": wl["params_name"]},
+                       "params": wl["params_name"], "host_affinity": affinity},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
                     "api": "vkt_bcn_cuda_compress == vierkant::bcn::compress(): pinned host source image in, stbir-exact resize chain + "
