@@ -70,6 +70,50 @@ static void run(const char *name, int ops_per_step, int ctas_per_sm, int sms, do
     const double per_clk_smsp = warp_inst / (best * 1e-3) / (mhz * 1e6) / (sms * 4.0);
     printf("%-34s %d CTAs/SM: %6.3f ms  %.3f warp-inst/clk/SMSP (counting %d inst per step)\n", name, ctas_per_sm, best, per_clk_smsp, ops_per_step);
 }
+// dependent-issue latency: ONE chain per thread, one warp per scheduler
+template<int OP>
+__global__ void __launch_bounds__(128) latency(uint32_t *out, int iters, uint32_t seed, uint32_t w)
+{
+    uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+#pragma unroll 1
+    for(int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for(int r = 0; r < 64; ++r)
+        {
+            if(OP == 0) { a = a * b + seed; }                                   // IMAD r*r+r
+            if(OP == 1) { a = a * w + b; }                                      // IMAD r*UR+r (w is a kernel parameter)
+            if(OP == 2) { a = __funnelshift_r(a, b, 8); }                       // SHF
+            if(OP == 3) { a = __viaddmin_s32((int) a, (int) b, 0x7FFFFFF0); }   // VIADDMNMX
+            if(OP == 4) { int d = __viaddmin_s32((int) a, (int) b, 0x7FFFFFF0) >> 8; a = (uint32_t) d * ((uint32_t) d * w) + a; }// the metric chain: VIADDMNMX, SHF, IMAD(UR), IMAD
+            if(OP == 5) { a = __dp4a(a, b, a); }                                // IDP.4A
+            if(OP == 6) { a = (a >= b) ? seed : a + 1; }                        // ISETP + SEL (+ IADD)
+        }
+    }
+    if(a == 0x12345u) { out[blockIdx.x * 128 + threadIdx.x] = a; }
+}
+template<int OP>
+static void lat(const char *name, int inst_per_step, int sms, double mhz, uint32_t *d)
+{
+    const int iters = 2000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    latency<OP><<<sms, 128>>>(d, 10, 1, 3);
+    cudaDeviceSynchronize();
+    float best = 1e9f;
+    for(int rep = 0; rep < 3; ++rep)
+    {
+        cudaEventRecord(e0);
+        latency<OP><<<sms, 128>>>(d, iters, 17 + rep, 103);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    const double cycles = best * 1e-3 * mhz * 1e6 / (double(iters) * 64);
+    printf("latency %-40s %.2f cycles per step (%d dependent instructions: %.2f each)\n", name, cycles, inst_per_step, cycles / inst_per_step);
+}
 int main()
 {
     cudaDeviceProp p;
@@ -80,6 +124,13 @@ int main()
     printf("%s, %d SMs, %.0f MHz (max)\n", p.name, p.multiProcessorCount, mhz);
     uint32_t *d;
     cudaMalloc(&d, 1 << 24);
+    lat<0>("IMAD r*r+r", 1, p.multiProcessorCount, mhz, d);
+    lat<1>("IMAD r*UR+r", 1, p.multiProcessorCount, mhz, d);
+    lat<2>("SHF", 1, p.multiProcessorCount, mhz, d);
+    lat<3>("VIADDMNMX", 1, p.multiProcessorCount, mhz, d);
+    lat<4>("VIADDMNMX > SHF > IMAD(UR) > IMAD", 4, p.multiProcessorCount, mhz, d);
+    lat<5>("IDP.4A", 1, p.multiProcessorCount, mhz, d);
+    lat<6>("ISETP > SEL (> IADD)", 3, p.multiProcessorCount, mhz, d);
     for(int c: {3, 8})
     {
         run<0>("IMAD r*r+r", 1, c, p.multiProcessorCount, mhz, d);

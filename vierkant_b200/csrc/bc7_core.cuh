@@ -309,6 +309,17 @@ struct Lane
     VKT_FN Texel at(int i) const { return p[i * STRIDE]; }
 };
 
+// Per-CTA exchange area behind the lane columns (device only): estimate_partition regroups the CTA's blocks by their
+// filterbank key through it.
+template<int STRIDE>
+struct CtaScratch
+{
+    uint32_t err[STRIDE];  // best estimator error so far (fits 32 bits when KEY28)
+    uint16_t info[STRIDE]; // best partition | running << 8
+    uint16_t perm[STRIDE]; // slot -> thread whose block the slot's thread adopts
+    uint32_t cnt[8][16];   // blocks per (thread index mod 8, key bin); zeroed by the kernel before its first barrier
+};
+
 // A colour cell = n texels of the block, listed by the nibbles of `perm` (texel index of cell element k at bits [4k,4k+4)).
 struct CellRef
 {
@@ -1306,15 +1317,63 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
 {
     const uint32_t total_partitions = umin(P.max_partitions, 64u);
     if(total_partitions <= 1) { return 0; }
-    constexpr uint32_t kUniformIters = 35;
+    constexpr uint32_t kUniformIters = 35, kKeyIters = 14;
     const uint32_t uniform_end = umin(total_partitions, kUniformIters);
     uint64_t best_err = kNoErr;
-    uint32_t best_partition = 0;
+    uint32_t best_partition = 0, best_it = 0;
     uint32_t key = 0;
     bool running = active;
+    Lane<STRIDE> Lc = L;// the block this lane is scoring (its own, until the regrouping below)
+#if defined(__CUDA_ARCH__)
+    // Filterbank phase (iterations 14..34): which candidates a block still needs depends only on its key partition -- the
+    // best of the first 14 (bc7enc.cpp:1786-1799, :1832-1833) -- and a warp pays for the union over its 32 blocks (21 of 21
+    // on average, where one block needs 14.2).  So at iteration 14 the CTA's blocks are regrouped by key: a counting sort
+    // through shared memory hands every lane the column pointer and the running state of another block, the warps run the
+    // phase on key-sorted batches (union 16.3 on the same data), and the results travel back the same way.  Which lane
+    // scores a block has no influence on the block's result.  All warps of the CTA reach this point (the early exit of
+    // the scan is held back until then), and the whole CTA calls estimate_partition exactly once.  Measured: -1.9 % kernel
+    // time (the three barriers eat most of the 13 % fewer candidates); keeping the adopted blocks for the rest of the
+    // kernel instead of sending results back was slower.
+    // (opaque kernels only: on the alpha kernels, 2 CTAs per SM, the barriers cost more than the smaller union saves)
+    const bool regroup = !M7 && KEY28 && (STRIDE == 256) && P.filterbank && (uniform_end > kKeyIters);// CTA-uniform
+    CtaScratch<STRIDE> *S = reinterpret_cast<CtaScratch<STRIDE> *>(L.p - threadIdx.x + 16 * STRIDE);
+    uint32_t src = threadIdx.x;
+    bool adopted = false;
+#else
+    const bool regroup = false;
+    (void) best_it;
+#endif
 #pragma unroll 1
     for(uint32_t it = 0; it < uniform_end; ++it)
     {
+#if defined(__CUDA_ARCH__)
+        if(regroup && it == kKeyIters)
+        {
+            running = running && (best_err > 0);
+            // Sorted within each class of thread index mod 8, and handed to a thread of the same class: lane columns are
+            // 16 bytes apart, so a quarter warp still covers all eight 16-byte bank groups and the 128-bit loads of the
+            // adopted columns stay conflict-free.  Class r's 32 blocks go, in key order, to lanes r, r+8, r+16, r+24 of
+            // warps 0, 1, ... 7.
+            const uint32_t bin = running ? best_it : 15u;// best_it < 14
+            const uint32_t cls = threadIdx.x & 7u;
+            const uint32_t pos = atomicAdd(&S->cnt[cls][bin], 1u);
+            S->err[threadIdx.x] = (uint32_t) best_err;// kNoErr -> 0xFFFFFFFF, above every real error (<= 2^32 - 16)
+            S->info[threadIdx.x] = (uint16_t) (best_partition | (running ? 256u : 0u));
+            __syncthreads();
+            uint32_t q = pos;
+#pragma unroll
+            for(uint32_t b = 0; b < 15; ++b) { q += (b < bin) ? S->cnt[cls][b] : 0u; }
+            constexpr uint32_t kPerWarp = 4;// lanes of one class in a warp
+            S->perm[(q / kPerWarp) * 32u + (q % kPerWarp) * 8u + cls] = (uint16_t) threadIdx.x;
+            __syncthreads();
+            src = S->perm[threadIdx.x];
+            const uint32_t e = S->err[src], info = S->info[src];
+            best_err = (e == 0xFFFFFFFFu) ? kNoErr : (uint64_t) e;
+            best_partition = info & 255u, key = best_partition, running = (info & 256u) != 0u;
+            Lc.p = L.p + ((int) src - (int) threadIdx.x);
+            adopted = true;
+        }
+#endif
         const uint32_t part = VKT_UTAB(order)[it];
         running = running && (best_err > 0);// loop condition of the reference
         bool need = running;
@@ -1328,18 +1387,32 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
         }
         if(!warp_any(need))
         {
-            if(!warp_any(running)) { break; }
+            if(!warp_any(running) && !(regroup && it < kKeyIters)) { break; }// (a warp must not leave before the regrouping)
             continue;
         }
-        const uint64_t err = estimate_pair<M7, PERC, KEY28, true, STRIDE>(T, P, L, part);
+        const uint64_t err = estimate_pair<M7, PERC, KEY28, true, STRIDE>(T, P, Lc, part);
         // bc7enc.cpp:1817-1820 with m_low_frequency_partition_weight == 1.0f (the only value the C ABI accepts) is the identity
         if(need)
         {
-            if(err < best_err) { best_err = err, best_partition = part; }
+            if(err < best_err) { best_err = err, best_partition = part, best_it = it; }
             if((part == 34) && (best_partition != 34)) { running = false; }
             if(it == 13) { key = best_partition; }
         }
     }
+#if defined(__CUDA_ARCH__)
+    if(regroup)// (CTA-uniform; `adopted` is true in every warp: the scan cannot end before iteration 14)
+    {
+        if(adopted)
+        {
+            S->err[src] = (best_err == kNoErr) ? 0xFFFFFFFFu : (uint32_t) best_err;
+            S->info[src] = (uint16_t) (best_partition | (running ? 256u : 0u));
+        }
+        __syncthreads();
+        const uint32_t e = S->err[threadIdx.x], info = S->info[threadIdx.x];
+        best_err = (e == 0xFFFFFFFFu) ? kNoErr : (uint64_t) e;
+        best_partition = info & 255u, running = (info & 256u) != 0u;
+    }
+#endif
     if(total_partitions > kUniformIters)
     {
         running = running && (best_err > 0);
@@ -1491,10 +1564,10 @@ VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[
 // Called by the whole converged warp; lanes with want == false only help the estimator.
 // Returns the weighted error, or kNoErr when not better than best_err.
 template<int MODE, bool PERC, bool KEY28, bool UBER, int STRIDE>
-VKT_FN uint64_t two_subset_trial(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool want, uint64_t best_err, BlockSolution &sol)
+VKT_FN uint64_t two_subset_cells(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part, bool want, uint64_t best_err,
+                                 BlockSolution &sol)
 {
     constexpr bool ALPHA = (MODE == 7);
-    const uint32_t part = estimate_partition<ALPHA, PERC, KEY28, STRIDE>(T, P, L, want);
     if(!want) { return kNoErr; }
     const uint32_t mask = T.part2[part];
     // element lists of the two subsets (ascending texel order, as the reference gathers them): nibble-packed work list
@@ -1650,6 +1723,15 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     sol.pbits[0] = sol.pbits[1] = 0;
     uint64_t best_err = kNoErr;
 
+    // The partition estimate (for mode 1 / mode 7) depends on the block alone.  Opaque blocks run it FIRST: nothing of the
+    // other modes is live during its loops (7 registers more for them at the 80-register budget; -2.7 % kernel time).  The
+    // reference runs it after mode 6 and skips it for blocks mode 6 already encodes exactly; here those few blocks estimate
+    // in vain.  Alpha blocks keep the reference's order (modes 6 and 5 often reach zero error on transparent blocks, and
+    // the skipped estimates are worth more than the registers: measured).
+    const bool do17 = ALPHA ? ((P.mode_mask & (1u << 7)) != 0) : ((P.max_partitions > 0) && (P.mode_mask & (1u << 1)));// warp-uniform
+    uint32_t part17 = 0;
+    if(!ALPHA && do17) { part17 = estimate_partition<false, PERC, KEY28, STRIDE>(T, P, L, true); }
+
     if(P.mode_mask & (1u << 6))
     {
         Cell c6;
@@ -1658,10 +1740,10 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     }
     if(!ALPHA)
     {
-        if((P.max_partitions > 0) && (P.mode_mask & (1u << 1)))// warp-uniform condition
+        if(do17)
         {
             BlockSolution s1 = sol;
-            if(two_subset_trial<1, PERC, KEY28, UBER, STRIDE>(T, P, L, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
+            if(two_subset_cells<1, PERC, KEY28, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
         }
     }
     else
@@ -1690,10 +1772,11 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
                 sol.pbits[0] = 0;
             }
         }
-        if(P.mode_mask & (1u << 7))// warp-uniform condition
+        if(do17)
         {
+            part17 = estimate_partition<true, PERC, KEY28, STRIDE>(T, P, L, best_err > 0);
             BlockSolution s7 = sol;
-            if(two_subset_trial<7, PERC, KEY28, UBER, STRIDE>(T, P, L, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
+            if(two_subset_cells<7, PERC, KEY28, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
         }
     }
     pack_block(T, sol, out);

@@ -17,7 +17,6 @@ struct Bc7Tables
 {
     // optimal single-colour endpoints, packed err | lo << 16 | hi << 24
     uint32_t opt1[256][2];// [colour][pbit]              bc7enc.cpp:213-240
-    uint32_t opt7[256][4];// [colour][hi_p * 2 + lo_p]   bc7enc.cpp:242-282
     float mid1[64][2];    // mode-1 6-bit+p quantiser midpoints   bc7enc.cpp:150-169
     float mid7[32][2];    // mode-7 5-bit+p                       bc7enc.cpp:129-148
     float mid5[128];      // mode-5 7-bit                         bc7enc.cpp:171-186
@@ -34,6 +33,8 @@ struct Bc7Tables
     uint8_t est_idx[64][16];
     uint8_t est_n0[64];
     float unit8[256];// v / 255.0f, the correctly rounded quotient find_optimal_solution divides out per component (bc7enc.cpp:1040-1042)
+    // LAST: only the alpha kernels (mode 7) read it; the opaque kernels copy the struct up to here into shared memory
+    uint32_t opt7[256][4];// [colour][hi_p * 2 + lo_p]   bc7enc.cpp:242-282
 };
 
 static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -154,6 +155,9 @@ __global__ void __launch_bounds__(256) bc7_classify_kernel(const __grid_constant
     }
 }
 
+__host__ __device__ constexpr size_t bc7_smem_table_bytes(bool alpha) { return alpha ? sizeof(Bc7Tables) : offsetof(Bc7Tables, opt7); }
+static_assert(offsetof(Bc7Tables, opt7) % 16 == 0, "table prefix is copied as uint4");
+
 // One lane == one block of the work list (list == nullptr: every block of the launch, in order).
 // UBER == false: the search without the uber-level stages (launched when uber_level == 0).
 template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int NT>
@@ -164,12 +168,16 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t n = count ? __ldg(count) : B.total_blocks;
     if(blockIdx.x * NT >= n) { return; }// the grid is sized for the whole launch; lists are usually shorter
+    // shared memory: [tables (opaque kernels: without the mode-7 table at their end)][lane columns][exchange area]
+    constexpr size_t kTab = bc7_smem_table_bytes(ALPHA);
     Bc7Tables &s_tables = *reinterpret_cast<Bc7Tables *>(s_raw);
-    Texel *s_lane = reinterpret_cast<Texel *>(s_raw + sizeof(Bc7Tables));// one 16-record column per lane (see Lane<>)
+    Texel *s_lane = reinterpret_cast<Texel *>(s_raw + kTab);// one 16-record column per lane (see Lane<>)
+    CtaScratch<NT> *s_scratch = reinterpret_cast<CtaScratch<NT> *>(s_lane + size_t(NT) * 16);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tables);
         uint4 *dst = reinterpret_cast<uint4 *>(&s_tables);
-        for(uint32_t i = threadIdx.x; i < sizeof(Bc7Tables) / 16; i += NT) { dst[i] = __ldg(src + i); }
+        for(uint32_t i = threadIdx.x; i < kTab / 16; i += NT) { dst[i] = __ldg(src + i); }
+        if(threadIdx.x < 128) { (&s_scratch->cnt[0][0])[threadIdx.x] = 0u; }
     }
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
     const uint32_t ii = min(i, n - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
@@ -184,12 +192,12 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm
     if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
-constexpr size_t kBc7SmemBytes = sizeof(Bc7Tables) + size_t(kBc7Threads) * 16 * sizeof(Texel);
+constexpr size_t bc7_smem_bytes(bool alpha) { return bc7_smem_table_bytes(alpha) + size_t(kBc7Threads) * 16 * sizeof(Texel) + sizeof(CtaScratch<kBc7Threads>); }
 
 template<bool PERC, bool KEY28, bool ALPHA, bool UBER>
 static cudaError_t bc7_kernel_attribute()
 {
-    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kBc7SmemBytes));
+    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bc7_smem_bytes(ALPHA)));
 }
 // > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
 static cudaError_t bc7_kernel_attributes()
@@ -381,7 +389,7 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
         B.total_blocks = uint32_t(total);
         const uint32_t grid = (B.total_blocks + kBc7Threads - 1) / kBc7Threads;
         auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
-            auto go = [&](auto kernel) { kernel<<<grid, kBc7Threads, kBc7SmemBytes, stream>>>(B, kp, s->d_tables, list, cnt); };
+            auto go = [&](auto kernel) { kernel<<<grid, kBc7Threads, bc7_smem_bytes(alpha), stream>>>(B, kp, s->d_tables, list, cnt); };
             // uber-free kernels exist for the 28-bit-key variants (every sane weight set); the wide-error ones always carry the stages
             const int sel = ((kp.uber_level == 0 && kp.key28) ? 8 : 0) | (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
             switch(sel)
