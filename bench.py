@@ -331,11 +331,24 @@ def main():
     import ctypes as C
     out_ptrs = (C.c_void_p * len(dims))(*[t.data_ptr() for t in host_out])
 
+    batch_srcs = None
+    if NTEX > 1:  # a material batch goes through vkt_bcn_cuda_compress_batch: whole chains, pipelined over two lanes per device
+        host_out_b = [[torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8).pin_memory() for (w, h) in dims] for _ in range(NTEX)]
+        out_ptrs_b = [(C.c_void_p * len(dims))(*[t.data_ptr() for t in ho]) for ho in host_out_b]
+        batch_srcs = []
+        for r in range(ROTATE):
+            arr = (capi.Source * NTEX)()
+            for j in range(NTEX):
+                arr[j] = capi.Source(host_levels[r * NTEX + j][0].data_ptr(), dims[0][0], dims[0][1], 4, capi.MODE_BC7, out_ptrs_b[j])
+            batch_srcs.append(arr)
+
     def step_e2e(i):
-        for j in range(NTEX):  # a material batch is one compress() per texture, as model::compress_textures calls it
-            src = host_levels[(i % ROTATE) * NTEX + j][0]  # the level-0 texture is the source image of the chain
-            ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
-                                                     C.byref(params), out_ptrs))
+        if batch_srcs is not None:
+            ctx._check(ctx.lib.vkt_bcn_cuda_compress_batch(ctx.handle, batch_srcs[i % ROTATE], NTEX, 1, C.byref(params)))
+            return
+        src = host_levels[i % ROTATE][0]  # the level-0 texture is the source image of the chain
+        ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                 C.byref(params), out_ptrs))
 
     def barrier():
         if world > 1:
@@ -418,8 +431,10 @@ def main():
                        "params": wl["params_name"], "host_affinity": affinity},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
-                    "api": "vkt_bcn_cuda_compress == vierkant::bcn::compress(): pinned host source image in, stbir-exact resize chain + "
-                           "classify + encode on the GPU, pinned host blocks of all levels out"},
+                    "api": ("vkt_bcn_cuda_compress == vierkant::bcn::compress(): pinned host source image in, stbir-exact resize chain + "
+                            "classify + encode on the GPU, pinned host blocks of all levels out") if NTEX == 1 else
+                           ("vkt_bcn_cuda_compress_batch: the textures of the batch, each as in vierkant::bcn::compress() (pinned source in, "
+                            "resize chain + encode on the GPU, pinned blocks out), pipelined over two lanes per device")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",

@@ -144,6 +144,22 @@ int vkt_bcn_cuda_compress_plan(uint32_t width, uint32_t height, int generate_mip
 int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
                           uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks);
 
+/* Several textures, each with its whole chain, in one call -- what model::compress_textures does texture by texture
+ * (src/model/model_loading.cpp:96-118).  Every device of the context works on two textures at a time
+ * (two sets of streams and buffers), so the upload and resizes of the next texture run under the encode kernels of the
+ * current one and no device idles between textures; textures go round-robin over the devices.  Results are identical
+ * to calling vkt_bcn_cuda_compress for each texture.  level_blocks[i] is the level_blocks argument of that call for
+ * texture i (vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps) gives its sizes). */
+typedef struct vkt_bcn_source
+{
+    const uint8_t *pixels;          /* tightly packed, row-major */
+    uint32_t width, height, comps;  /* comps: 3 or 4 */
+    uint32_t mode;                  /* VKT_BCN_MODE_* (a material mixes BC7 colour maps and BC5 normal maps) */
+    void *const *level_blocks;
+} vkt_bcn_source;
+int vkt_bcn_cuda_compress_batch(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32_t num_sources, int generate_mipmaps,
+                                const vkt_bc7_params *params);
+
 /* Counters for the measurement harness: kernels launched / bytes copied by this context since creation. */
 typedef struct vkt_bcn_stats
 {

@@ -14,6 +14,7 @@
 //   * duration is the whole call in milliseconds, never 0: the reference's own test asserts duration > 0 ms
 //     (tests/TestCompressionBC7.cpp:48) and a GPU call can finish in less than one
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -22,6 +23,7 @@
 
 #include <vierkant/texture_block_compression.hpp>
 
+#include "texture_block_compression_batch.hpp"
 #include "vierkant_bcn_cuda.h"
 
 namespace vierkant::bcn
@@ -44,11 +46,16 @@ struct cuda_context_t
     cuda_context_t(const cuda_context_t &) = delete;
     cuda_context_t &operator=(const cuda_context_t &) = delete;
 };
+cuda_context_t &shared_context()
+{
+    static cuda_context_t context;// thread-safe magic static, as in the reference (:66)
+    return context;
+}
 }// namespace
 
 compress_result_t compress(const compress_info_t &compress_info)
 {
-    static cuda_context_t context;// thread-safe magic static, as in the reference (:66)
+    cuda_context_t &context = shared_context();
 
     auto image = std::dynamic_pointer_cast<const crocore::Image_<uint8_t>>(compress_info.image);
     if(!image || image->num_components() < 3)
@@ -86,6 +93,52 @@ compress_result_t compress(const compress_info_t &compress_info)
     auto elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start_time);
     ret.duration = std::max(elapsed, std::chrono::milliseconds(1));
     return ret;
+}
+
+std::vector<compress_result_t> compress(std::span<const compress_info_t> compress_infos)
+{
+    cuda_context_t &context = shared_context();
+    auto start_time = std::chrono::steady_clock::now();
+    const size_t n = compress_infos.size();
+    std::vector<compress_result_t> results(n);
+    std::vector<std::array<void *, 16>> level_ptrs(n);
+    std::vector<vkt_bcn_source> sources(n);
+    bool mipmaps = n ? compress_infos[0].generate_mipmaps : false;
+    for(size_t i = 0; i < n; ++i)
+    {
+        const compress_info_t &info = compress_infos[i];
+        auto image = std::dynamic_pointer_cast<const crocore::Image_<uint8_t>>(info.image);
+        if(!image || image->num_components() < 3)
+        {
+            throw std::invalid_argument("vierkant::bcn::compress: expected 8-bit images with 3 or 4 components");
+        }
+        if(info.generate_mipmaps != mipmaps) { throw std::invalid_argument("vierkant::bcn::compress: one mipmap setting per batch"); }
+        vkt_bcn_plan plan = {};
+        if(vkt_bcn_cuda_compress_plan(image->width(), image->height(), mipmaps ? 1 : 0, &plan) != VKT_BCN_OK)
+        {
+            throw std::invalid_argument("vierkant::bcn::compress: empty image");
+        }
+        compress_result_t &ret = results[i];
+        ret.mode = info.mode;
+        ret.base_width = plan.base_width;
+        ret.base_height = plan.base_height;
+        ret.levels.resize(plan.num_levels);
+        level_ptrs[i].fill(nullptr);
+        for(uint32_t l = 0; l < plan.num_levels; ++l)
+        {
+            ret.levels[l].resize(plan.level_num_blocks[l]);
+            level_ptrs[i][l] = ret.levels[l].data();
+        }
+        sources[i] = {static_cast<const uint8_t *>(image->data()), image->width(), image->height(), image->num_components(),
+                      info.mode == BC7 ? uint32_t(VKT_BCN_MODE_BC7) : uint32_t(VKT_BCN_MODE_BC5), level_ptrs[i].data()};
+    }
+    if(vkt_bcn_cuda_compress_batch(context.ctx, sources.data(), uint32_t(n), mipmaps ? 1 : 0, nullptr) != VKT_BCN_OK)
+    {
+        throw std::runtime_error(std::string("vierkant::bcn::compress (CUDA, batch): ") + vkt_bcn_cuda_last_error(context.ctx));
+    }
+    auto elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start_time);
+    for(auto &r: results) { r.duration = std::max(elapsed, std::chrono::milliseconds(1)); }// the batch's time: textures overlap
+    return results;
 }
 
 }// namespace vierkant::bcn

@@ -110,3 +110,25 @@ def test_compress_with_parameters(ctx, port_oracle):
     _, levels = ctx.compress(img, capi.MODE_BC7, True, capi.default_params(**kw))
     for got, ref in zip(levels, want["levels"]):
         assert np.array_equal(got, ref)
+
+
+def test_compress_batch_matches_per_texture_calls(ctx, port_oracle):
+    """vkt_bcn_cuda_compress_batch: several textures of different sizes / component counts / modes, chains
+    pipelined over two lanes of the device; every level identical to a vkt_bcn_cuda_compress call per texture."""
+    imgs = [synth.make_texture(512, 256, 0, seed=1), synth.make_texture(260, 124, 1, seed=2), synth.make_texture(64, 64, 1, seed=3)[..., :3],
+            synth.make_texture(1024, 1024, 1, seed=4), synth.make_texture(36, 20, 0, seed=5), synth.make_texture(256, 256, 0, seed=6),
+            synth.make_texture(128, 512, 1, seed=7)]
+    modes = [capi.MODE_BC7, capi.MODE_BC7, capi.MODE_BC7, capi.MODE_BC7, capi.MODE_BC5, capi.MODE_BC7, capi.MODE_BC5]
+    got = ctx.compress_batch(imgs, modes, True)
+    for im, mode, levels in zip(imgs, modes, got):
+        _, want = ctx.compress(im, mode, True)
+        assert len(levels) == len(want)
+        for a, b in zip(levels, want):
+            assert np.array_equal(a, b)
+    ref = port_oracle.compress(imgs[1], 1, True, threads=os.cpu_count() or 1)
+    for a, b in zip(got[1], ref["levels"]):
+        assert np.array_equal(a, b)
+    # no mips, and an empty batch
+    single = ctx.compress_batch(imgs[:3], capi.MODE_BC7, False)
+    assert [len(l) for l in single] == [1, 1, 1] and np.array_equal(single[0][0], got[0][0])
+    assert ctx.compress_batch([], capi.MODE_BC7, True) == []

@@ -98,3 +98,25 @@ def test_dropin_matches_reference_build(ref_oracle):
     assert len(got["levels"]) == len(want["levels"])
     for a, b in zip(got["levels"], want["levels"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_dropin_batch_overload_matches_single_calls():
+    """vierkant::bcn::compress(std::span<const compress_info_t>) (integration/texture_block_compression_batch.hpp): the
+    textures of a model in one call return what the per-texture calls return."""
+    L = _load()
+    L.dropin_compress_pair.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    L.dropin_compress_pair.restype = C.c_void_p
+    a = np.ascontiguousarray(synth.make_texture(200, 120, 1, seed=5))
+    b = np.ascontiguousarray(synth.make_texture(64, 256, 0, seed=6))
+    for which, img in ((0, a), (1, b)):
+        r = L.dropin_compress_pair(a.ctypes.data, 200, 120, b.ctypes.data, 64, 256, 4, 1, 1, which)
+        try:
+            want = _compress(L, img, 1, True)
+            assert L.dropin_result_num_levels(r) == len(want["levels"]) and L.dropin_result_duration_ms(r) > 0
+            for l, ref in enumerate(want["levels"]):
+                n = L.dropin_result_level_blocks(r, l)
+                buf = (C.c_uint8 * (16 * n)).from_address(L.dropin_result_level_data(r, l))
+                assert np.array_equal(np.frombuffer(buf, dtype=np.uint8).reshape(n, 16), ref)
+        finally:
+            L.dropin_result_free(r)

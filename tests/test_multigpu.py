@@ -56,6 +56,17 @@ def test_compress_chain_big_split_over_devices(ctx, multi_ctx, known_2048):
     assert "%016x" % synth.fnv1a64_words(np.concatenate(a)) == known_2048
 
 
+def test_compress_batch_over_devices(ctx, multi_ctx):
+    """Whole chains of several textures, round-robin over the devices (two lanes each): identical to one device."""
+    imgs = [synth.make_texture(512 >> (i % 3), 256, i & 1, seed=30 + i) for i in range(11)]
+    a = multi_ctx.compress_batch(imgs, capi.MODE_BC7, True)
+    b = ctx.compress_batch(imgs, capi.MODE_BC7, True)
+    for la, lb in zip(a, b):
+        assert len(la) == len(lb)
+        for x, y in zip(la, lb):
+            assert np.array_equal(x, y)
+
+
 def test_batch_of_textures_over_devices(ctx, multi_ctx):
     imgs = [synth.make_texture(256 >> (i % 3), 128, i & 1, seed=10 + i) for i in range(9)]
     outs_a = [np.empty(((i.shape[0] // 4) * (i.shape[1] // 4), 16), dtype=np.uint8) for i in imgs]

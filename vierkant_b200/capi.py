@@ -48,6 +48,12 @@ class Plan(C.Structure):
                 ("level_num_blocks", C.c_uint64 * 16)]
 
 
+class Source(C.Structure):
+    """vkt_bcn_source"""
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("comps", C.c_uint32), ("mode", C.c_uint32),
+                ("level_blocks", C.POINTER(C.c_void_p))]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
@@ -57,7 +63,7 @@ EXPORTS = [
     "vkt_bcn_cuda_num_devices", "vkt_bcn_cuda_last_error", "vkt_bcn_cuda_encode_bc7", "vkt_bcn_cuda_encode_bc5",
     "vkt_bcn_cuda_encode_batch", "vkt_bcn_cuda_encode_bc7_device", "vkt_bcn_cuda_encode_bc5_device",
     "vkt_bcn_cuda_resize_u8", "vkt_bcn_cuda_compress_plan", "vkt_bcn_cuda_compress", "vkt_bcn_cuda_get_stats",
-    "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device",
+    "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device", "vkt_bcn_cuda_compress_batch",
 ]
 
 _lib = None
@@ -92,6 +98,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.vkt_bcn_cuda_resize_u8.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32]
     L.vkt_bcn_cuda_compress_plan.argtypes = [u32, u32, C.c_int, C.POINTER(Plan)]
     L.vkt_bcn_cuda_compress.argtypes = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), C.POINTER(vp)]
+    L.vkt_bcn_cuda_compress_batch.argtypes = [vp, C.POINTER(Source), u32, C.c_int, C.POINTER(Bc7Params)]
     L.vkt_bcn_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.vkt_bcn_cuda_measure_issue_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     if path == _build.CUDA_SO:
@@ -241,6 +248,25 @@ class BcnContext:
         pp = C.byref(params) if params is not None else None
         self._check(self.lib.vkt_bcn_cuda_compress(self.handle, mode, _ptr(img), w, h, c, int(generate_mipmaps), pp, ptrs))
         return plan, levels
+
+    def compress_batch(self, imgs: list, modes: int | list = MODE_BC7, generate_mipmaps: bool = True,
+                       params: Bc7Params | None = None) -> list[list[np.ndarray]]:
+        """vkt_bcn_cuda_compress_batch: every texture's whole chain, textures pipelined over two lanes per device."""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in imgs]
+        modes = [modes] * len(imgs) if isinstance(modes, int) else list(modes)
+        srcs = (Source * len(imgs))()
+        outs, keep = [], []
+        for i, im in enumerate(imgs):
+            h, w, c = im.shape
+            plan = compress_plan(w, h, generate_mipmaps)
+            levels = [np.empty((int(plan.level_num_blocks[l]), 16), dtype=np.uint8) for l in range(plan.num_levels)]
+            ptrs = (C.c_void_p * plan.num_levels)(*[_ptr(l) for l in levels])
+            keep.append(ptrs)
+            srcs[i] = Source(_ptr(im), w, h, c, modes[i], ptrs)
+            outs.append(levels)
+        pp = C.byref(params) if params is not None else None
+        self._check(self.lib.vkt_bcn_cuda_compress_batch(self.handle, srcs, len(imgs), int(generate_mipmaps), pp))
+        return outs
 
     # ---- device buffers (kernel only) ---------------------------------------------------------------------------
     def encode_bc7_device(self, d_pixels, width: int, height: int, comps: int, d_out, params: Bc7Params | None = None,

@@ -273,6 +273,8 @@ struct DeviceSlot
 struct vkt_bcn_ctx
 {
     std::vector<vkt::DeviceSlot *> slots;
+    std::vector<vkt::DeviceSlot *> slots2;// second set of streams / buffers per device (compress_batch), made on first use
+    vkt::Bc7Tables host_tables;
     std::string last_error;
     std::mutex err_mtx;
     vkt_bcn_stats stats{};
@@ -464,6 +466,37 @@ static int launch_bc5(vkt_bcn_ctx *ctx, DeviceSlot *s, const void *d_px, uint32_
 
 }// namespace vkt
 
+// streams, tables and kernel attributes of one slot (a device, or a device's second lane)
+static cudaError_t init_slot(vkt::DeviceSlot *s, const vkt::Bc7Tables &host_tables)
+{
+    using namespace vkt;
+    const int dev = s->device;
+        cudaError_t e = cudaSetDevice(dev);
+    // `stream` carries the (cheap) resize kernels of the pipelined chain: highest priority, so that their CTAs are placed
+    // ahead of the pending CTAs of the long encode kernels running on the other lanes
+    int prio_lo = 0, prio_hi = 0;
+    if(e == cudaSuccess) { e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream5, cudaStreamNonBlocking); }
+    if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream6, cudaStreamNonBlocking); }
+    if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
+    if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
+    if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
+    if(e == cudaSuccess)
+    {
+        // the per-launch work lists come from the stream-ordered allocator: keep freed blocks cached in the pool
+        // instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        uint64_t keep = ~0ull;
+        if(e == cudaSuccess) { e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    }
+    return e;
+}
+
 #include "resize_core.cuh"
 
 using namespace vkt;
@@ -495,8 +528,7 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
     }
     auto *ctx = new(std::nothrow) vkt_bcn_ctx;
     if(!ctx) { return VKT_BCN_ERR_OOM; }
-    Bc7Tables host_tables;
-    bc7_tables_build(&host_tables);
+    bc7_tables_build(&ctx->host_tables);
     {
         // the compile-time uber-level selector maps (bc7_core.cuh) against the reference's float expression
         const UberMaps um = make_uber_maps();
@@ -528,29 +560,7 @@ int vkt_bcn_cuda_create(vkt_bcn_ctx **out_ctx, const int *devices, int num_devic
         auto *s = new DeviceSlot;
         s->device = dev;
         ctx->slots.push_back(s);
-        cudaError_t e = cudaSetDevice(dev);
-        // `stream` carries the (cheap) resize kernels of the pipelined chain: highest priority, so that their CTAs are placed
-        // ahead of the pending CTAs of the long encode kernels running on the other lanes
-        int prio_lo = 0, prio_hi = 0;
-        if(e == cudaSuccess) { e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream5, cudaStreamNonBlocking); }
-        if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream6, cudaStreamNonBlocking); }
-        if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
-        if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
-        if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
-        if(e == cudaSuccess)
-        {
-            // the per-launch work lists come from the stream-ordered allocator: keep freed blocks cached in the pool
-            // instead of returning them to the driver at every synchronisation
-            cudaMemPool_t pool = nullptr;
-            e = cudaDeviceGetDefaultMemPool(&pool, dev);
-            uint64_t keep = ~0ull;
-            if(e == cudaSuccess) { e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
-        }
+        const cudaError_t e = init_slot(s, ctx->host_tables);
         if(e != cudaSuccess)
         {
             fail(nullptr, VKT_BCN_ERR_CUDA, "device %d initialisation failed: %s", dev, cudaGetErrorString(e));
@@ -566,7 +576,9 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
 {
     if(!ctx) { return; }
     if(ctx->h_stage) { cudaFreeHost(ctx->h_stage); }
-    for(auto *s: ctx->slots)
+    std::vector<vkt::DeviceSlot *> all(ctx->slots);
+    all.insert(all.end(), ctx->slots2.begin(), ctx->slots2.end());
+    for(auto *s: all)
     {
         if(cudaSetDevice(s->device) == cudaSuccess)
         {
@@ -881,6 +893,14 @@ int vkt_bcn_cuda_resize_u8(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t wid
 {
     if(!ctx) { return VKT_BCN_ERR_INVALID; }
     return resize_host(ctx, pixels, width, height, comps, out_pixels, out_width, out_height);
+}
+
+int vkt_bcn_cuda_compress_batch(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32_t num_sources, int generate_mipmaps,
+                                const vkt_bc7_params *params)
+{
+    if(!ctx) { return VKT_BCN_ERR_INVALID; }
+    if(num_sources && !sources) { return fail(ctx, VKT_BCN_ERR_INVALID, "null source list"); }
+    return compress_many(ctx, sources, num_sources, generate_mipmaps, params);
 }
 
 int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,

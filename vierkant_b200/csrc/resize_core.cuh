@@ -242,8 +242,11 @@ static int resize_host(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t w, uint
 // The whole of vierkant::bcn::compress() (src/texture_block_compression.cpp:64-154).  Every device of the context
 // uploads the source, runs the (cheap) resize chain itself and encodes its share of every level's block rows, so no
 // device-to-device traffic is needed ("halo recompute" taken to the whole chain).
-static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
-                          int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks)
+// Queue one chain on `slots` (one slot per participating device; the caller holds their mutexes).  Nothing is waited for:
+// chain_wait() does that.
+static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots, uint32_t mode, const uint8_t *pixels, uint32_t width,
+                         uint32_t height, uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks,
+                         std::vector<std::pair<cudaEvent_t, std::string>> *marks_out)
 {
     if(mode != VKT_BCN_MODE_BC7 && mode != VKT_BCN_MODE_BC5) { return fail(ctx, VKT_BCN_ERR_INVALID, "unknown mode %u", mode); }
     if(!pixels || !level_blocks || !width || !height) { return fail(ctx, VKT_BCN_ERR_INVALID, "null buffer or empty image"); }
@@ -262,7 +265,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         const int rc = bc7_prepare_params(params ? params : &def, &kp);
         if(rc) { return fail(ctx, rc, rc == VKT_BCN_ERR_UNSUPPORTED ? "unsupported bc7 parameters" : "invalid bc7 parameters"); }
     }
-    const uint32_t G = uint32_t(ctx->slots.size());
+    const uint32_t G = uint32_t(slots.size());
     const size_t src_bytes = size_t(width) * height * comps;
     size_t lvl_off[16], lvl_total = 0, out_off[16], out_total = 0;
     for(uint32_t l = 0; l < plan.num_levels; ++l)
@@ -271,8 +274,6 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         lvl_total += align_up(size_t(plan.level_width[l]) * plan.level_height[l] * comps, 256);
         out_total += align_up(size_t(plan.level_num_blocks[l]) * 16, 256);
     }
-    std::vector<std::unique_lock<std::mutex>> locks;
-    for(uint32_t g = 0; g < G; ++g) { locks.emplace_back(ctx->slots[g]->mtx); }
     int rc = VKT_BCN_OK;
     // Level 0 is pipelined in row bands over several streams per device -- upload (stream2) -> resize (stream, high
     // priority) -> encode (stream4/5/6 round robin, so the tail wave of one band overlaps the heads of the next ones) ->
@@ -343,7 +344,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     }
     for(uint32_t g = 0; g < Geff && !rc; ++g)
     {
-        DeviceSlot *s = ctx->slots[g];
+        DeviceSlot *s = slots[g];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
         ev_slot = s, s->events_used = 0;
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
@@ -505,7 +506,7 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     if(tail && !rc)
     {
         // small levels [M, L) on device 0: wait for every device's rows of level M-1, fetch them, continue the chain
-        DeviceSlot *s = ctx->slots[0];
+        DeviceSlot *s = slots[0];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
         ev_slot = s;
         uint8_t *d_lvl = static_cast<uint8_t *>(s->d_in) + align_up(src_bytes, 256);
@@ -540,9 +541,15 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
             count(ctx, 0, 0, bytes);
         }
     }
-    for(uint32_t g = 0; g < G; ++g)
+    if(marks_out) { marks_out->swap(marks); }
+    return rc;
+}
+
+static int chain_wait(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots)
+{
+    int rc = VKT_BCN_OK;
+    for(DeviceSlot *s: slots)
     {
-        DeviceSlot *s = ctx->slots[g];
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
         cudaError_t e = cudaStreamSynchronize(s->stream);
         for(cudaStream_t st: {s->stream2, s->stream3, s->stream4, s->stream5, s->stream6})
@@ -552,12 +559,66 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         }
         if(e != cudaSuccess && !rc) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
     }
-    if(trace && !marks.empty() && G == 1)
+    return rc;
+}
+
+// The whole of vierkant::bcn::compress() for one image on every device of the context.
+static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                          int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks)
+{
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    std::vector<std::pair<cudaEvent_t, std::string>> marks;
+    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, &marks);
+    const int rw = chain_wait(ctx, ctx->slots);
+    if(!rc) { rc = rw; }
+    if(!marks.empty() && ctx->slots.size() == 1)// VKT_BCN_TRACE=1
     {
         for(const auto &m: marks)
         {
             float ms = 0.0f;
             if(cudaEventElapsedTime(&ms, marks[0].first, m.first) == cudaSuccess) { fprintf(stderr, "[vkt trace] %8.3f ms  %s\n", ms, m.second.c_str()); }
+        }
+    }
+    return rc;
+}
+
+// Several textures (vkt_bcn_cuda_compress_batch): two lanes per device -- the primary slot and a second one with its own
+// streams and buffers -- each taking whole chains in turn.  The host only waits for a lane when it wants to reuse it, and by
+// then the other lane of that device has a complete chain queued, so the device never idles between textures.
+static int compress_many(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32_t n, int generate_mipmaps, const vkt_bc7_params *params)
+{
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    const size_t G = ctx->slots.size();
+    while(ctx->slots2.size() < G)
+    {
+        auto *s = new DeviceSlot;
+        s->device = ctx->slots[ctx->slots2.size()]->device;
+        ctx->slots2.push_back(s);
+        const cudaError_t e = init_slot(s, ctx->host_tables);
+        if(e != cudaSuccess) { return fail(ctx, VKT_BCN_ERR_CUDA, "second lane of device %d: %s", s->device, cudaGetErrorString(e)); }
+    }
+    std::vector<std::vector<DeviceSlot *>> lanes;// lane k: device k % G, set k / G
+    for(size_t k = 0; k < 2 * G; ++k) { lanes.push_back({(k < G) ? ctx->slots[k] : ctx->slots2[k - G]}); }
+    std::vector<char> busy(lanes.size(), 0);
+    int rc = VKT_BCN_OK;
+    for(uint32_t t = 0; t < n && !rc; ++t)
+    {
+        const size_t k = t % lanes.size();
+        if(busy[k]) { rc = chain_wait(ctx, lanes[k]); }
+        busy[k] = 0;
+        if(rc) { break; }
+        const vkt_bcn_source &src = sources[t];
+        rc = chain_enqueue(ctx, lanes[k], src.mode, src.pixels, src.width, src.height, src.comps, generate_mipmaps, params, src.level_blocks, nullptr);
+        busy[k] = 1;
+    }
+    for(size_t k = 0; k < lanes.size(); ++k)
+    {
+        if(busy[k])
+        {
+            const int rw = chain_wait(ctx, lanes[k]);
+            if(!rc) { rc = rw; }
         }
     }
     return rc;
