@@ -71,6 +71,18 @@ int emul_chain_plan(const uint32_t *level_height, uint32_t num_levels, uint32_t 
     return int(split.sliced | (split.devices << 8));
 }
 
+// number of u8 values whose division-free decode (resize_decode_u8) differs from the reference's v / 255.0f
+int emul_resize_decode_mismatches()
+{
+    int bad = 0;
+    for(uint32_t v = 0; v < 256; ++v)
+    {
+        volatile float want = (float) v / 255.0f;
+        bad += vkt::resize_decode_u8(v) != want;
+    }
+    return bad;
+}
+
 // number of (max, ly, hy) cells whose compile-time uber selector map differs from the reference's float expression
 int emul_uber_map_mismatches()
 {

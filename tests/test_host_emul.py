@@ -61,6 +61,11 @@ def test_unsupported_knobs_are_rejected(emul, kw):
     assert rc == -2
 
 
+def test_resize_decode_is_the_exact_quotient(emul):
+    """The resize passes decode u8 / 255.0f with one Newton step instead of a division: exact for all 256 values."""
+    assert emul.lib.emul_resize_decode_mismatches() == 0
+
+
 RESIZE_SHAPES = [(64, 64, 64, 64, 4), (64, 64, 32, 32, 4), (123, 81, 124, 84, 4), (256, 128, 16, 8, 4), (60, 36, 60, 36, 3),
                  (4, 4, 512, 256, 4), (100, 52, 52, 28, 4), (124, 84, 64, 44, 4), (8, 4, 4, 4, 4), (4, 4, 4, 4, 4), (12, 20, 8, 12, 3),
                  (33, 7, 36, 8, 1), (50, 50, 200, 30, 2), (17, 300, 20, 150, 4), (640, 8, 320, 4, 4), (1024, 16, 512, 8, 4),

@@ -9,6 +9,27 @@ namespace vkt
 {
 
 // ------------------------------------------------------------------------------------------------ host: tap lists
+#if defined(__CUDACC__)
+#define VKT_RESIZE_HD __host__ __device__
+#else
+#define VKT_RESIZE_HD
+#endif
+// stbir decodes a sample as u8 / 255.0f (:1252-1291).  The correctly rounded quotient without a division: one Newton step on
+// v * (1/255) -- q1 = fma(fma(-q0, 255, v), 1/255, q0) -- equals v / 255.0f for all 256 values (checked exhaustively in
+// tests/test_host_emul.py); four FMA-pipe instructions instead of a ~10-instruction IEEE division or a shared-memory
+// lookup (the pass is bound by its load/store instructions).
+VKT_RESIZE_HD inline float resize_decode_u8(uint32_t v)
+{
+    const float fv = (float) v, r = 1.0f / 255.0f;
+#if defined(__CUDA_ARCH__)
+    const float q0 = __fmul_rn(fv, r);
+    return __fmaf_rn(__fmaf_rn(-q0, 255.0f, fv), r, q0);
+#else
+    const float q0 = fv * r;
+    return fmaf(fmaf(-q0, 255.0f, fv), r, q0);
+#endif
+}
+
 struct ResizeAxis
 {
     int in_size = 0, out_size = 0;

@@ -30,30 +30,26 @@ namespace vkt
 struct DeviceAxis
 {
     int in_size = 0, out_size = 0;
-    int *d_start = nullptr, *d_idx = nullptr;
-    float *d_coef = nullptr;
+    int *d_start = nullptr;
+    int2 *d_tap = nullptr;// {input sample, coefficient bits}: one 64-bit load per tap
     std::vector<int> first_in, last_in;// per output: smallest / largest input sample (band planning)
     ~DeviceAxis()
     {
         cudaFree(d_start);
-        cudaFree(d_idx);
-        cudaFree(d_coef);
+        cudaFree(d_tap);
     }
 };
 
 // ------------------------------------------------------------------------------------------------ device passes
-// Horizontal pass: rows [row0, row0 + rows) of the source -> fp32 band, one thread per (row, output column).
+constexpr int kResizeTileW = 32, kResizeTileH = 8;// threads of a 256-thread CTA as a tile of output samples
+// Horizontal pass: rows [row0, row0 + rows) of the source -> fp32 band, one thread per (row, output column); a CTA is a
+// 32-column x 8-row tile, so its eight rows share their tap lists through L1.  (Decoding the tile's source run once into
+// shared memory instead of per tap was measured slower: the pass is bound by its loads, not by the decode arithmetic.)
 template<int C>
 __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict__ src, int in_w, int row0, int rows, int out_w,
-                                                        const int *__restrict__ start, const int *__restrict__ idx,
-                                                        const float *__restrict__ coef, float *__restrict__ band)
+                                                        const int *__restrict__ start, const int2 *__restrict__ tap, float *__restrict__ band)
 {
-    // stbir decodes a sample as u8 / 255.0f (:1252-1291): one correctly rounded division per value, taken from a table of
-    // the 256 quotients instead of being redone per tap and channel (the pass is otherwise bound by those divisions)
-    __shared__ float s_decode[256];
-    s_decode[threadIdx.x] = __fdiv_rn((float) threadIdx.x, 255.0f);
-    __syncthreads();
-    const int x = blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
+    const int x = blockIdx.x * kResizeTileW + int(threadIdx.x % kResizeTileW), r = blockIdx.y * kResizeTileH + int(threadIdx.x / kResizeTileW);
     if(x >= out_w || r >= rows) { return; }
     const uint8_t *row = src + size_t(row0 + r) * size_t(in_w) * C;
     float acc[C];
@@ -62,8 +58,9 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
     const int t1 = __ldg(start + x + 1);
     for(int t = __ldg(start + x); t < t1; ++t)
     {
-        const uint8_t *p = row + size_t(__ldg(idx + t)) * C;
-        const float w = __ldg(coef + t);
+        const int2 tp = __ldg(tap + t);
+        const uint8_t *p = row + size_t(tp.x) * C;
+        const float w = __int_as_float(tp.y);
         uint32_t v[C];
         if(C == 4)
         {
@@ -76,7 +73,7 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
             for(int c = 0; c < C; ++c) { v[c] = p[c]; }
         }
 #pragma unroll
-        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(s_decode[v[c]], w)); }
+        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(resize_decode_u8(v[c]), w)); }
     }
     float *o = band + (size_t(r) * size_t(out_w) + size_t(x)) * C;
 #pragma unroll
@@ -86,19 +83,22 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
 // Vertical pass + encode: output rows [y0, y0 + rows), one thread per (output row, column).
 template<int C>
 __global__ void __launch_bounds__(256) resize_v_kernel(const float *__restrict__ band, int band_row0, int out_w, int y0, int rows,
-                                                        const int *__restrict__ start, const int *__restrict__ idx,
-                                                        const float *__restrict__ coef, uint8_t *__restrict__ dst)
+                                                        const int *__restrict__ start, const int2 *__restrict__ tap, uint8_t *__restrict__ dst)
 {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = y0 + blockIdx.y;
-    if(x >= out_w || int(blockIdx.y) >= rows) { return; }
+    // 32 x 8 tile: neighbouring output rows read mostly the same band rows (5 of 5 taps shifted by one at 1:1), which then
+    // come from L1 instead of L2
+    const int x = blockIdx.x * kResizeTileW + int(threadIdx.x % kResizeTileW), ry = blockIdx.y * kResizeTileH + int(threadIdx.x / kResizeTileW);
+    const int y = y0 + ry;
+    if(x >= out_w || ry >= rows) { return; }
     float acc[C];
 #pragma unroll
     for(int c = 0; c < C; ++c) { acc[c] = 0.0f; }
     const int t1 = __ldg(start + y + 1);
     for(int t = __ldg(start + y); t < t1; ++t)
     {
-        const float *p = band + (size_t(__ldg(idx + t) - band_row0) * size_t(out_w) + size_t(x)) * C;
-        const float w = __ldg(coef + t);
+        const int2 tp = __ldg(tap + t);
+        const float *p = band + (size_t(tp.x - band_row0) * size_t(out_w) + size_t(x)) * C;
+        const float w = __int_as_float(tp.y);
 #pragma unroll
         for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(p[c], w)); }
     }
@@ -150,11 +150,16 @@ static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, const Devi
     d->in_size = in, d->out_size = out;
     const size_t n = h.idx.size();
     VKT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d->d_start), (size_t(out) + 1) * sizeof(int)));
-    VKT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d->d_idx), std::max<size_t>(n, 1) * sizeof(int)));
-    VKT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d->d_coef), std::max<size_t>(n, 1) * sizeof(float)));
+    VKT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d->d_tap), std::max<size_t>(n, 1) * sizeof(int2)));
+    std::vector<int2> taps(n);
+    for(size_t t = 0; t < n; ++t)
+    {
+        int bits;
+        memcpy(&bits, &h.coef[t], sizeof(bits));
+        taps[t] = make_int2(h.idx[t], bits);
+    }
     VKT_CUDA(ctx, cudaMemcpyAsync(d->d_start, h.start.data(), (size_t(out) + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    VKT_CUDA(ctx, cudaMemcpyAsync(d->d_idx, h.idx.data(), n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    VKT_CUDA(ctx, cudaMemcpyAsync(d->d_coef, h.coef.data(), n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    VKT_CUDA(ctx, cudaMemcpyAsync(d->d_tap, taps.data(), n * sizeof(int2), cudaMemcpyHostToDevice, s->stream));
     VKT_CUDA(ctx, cudaStreamSynchronize(s->stream));// the host vectors die with this scope
     d->first_in.resize(size_t(out)), d->last_in.resize(size_t(out));
     for(int o = 0; o < out; ++o)
@@ -198,13 +203,14 @@ static int resize_device(vkt_bcn_ctx *ctx, DeviceSlot *s, const uint8_t *d_src, 
         const int rows_in = r_hi - r_lo + 1;
         if((rc = ensure(ctx, &s->d_tmp, &s->tmp_cap, size_t(rows_in) * row_bytes))) { return rc; }
         float *band = static_cast<float *>(s->d_tmp);
-        const dim3 gh((ow + 255) / 256, uint32_t(rows_in)), gv((ow + 255) / 256, y1 - y0);
+        const dim3 gh((ow + kResizeTileW - 1) / kResizeTileW, (uint32_t(rows_in) + kResizeTileH - 1) / kResizeTileH),
+                gv((ow + kResizeTileW - 1) / kResizeTileW, (y1 - y0 + kResizeTileH - 1) / kResizeTileH);
         switch(comps)
         {
 #define VKT_RESIZE_CASE(C)                                                                                                     \
     case C:                                                                                                                    \
-        resize_h_kernel<C><<<gh, 256, 0, stream>>>(d_src, int(w), r_lo, rows_in, int(ow), ax->d_start, ax->d_idx, ax->d_coef, band); \
-        resize_v_kernel<C><<<gv, 256, 0, stream>>>(band, r_lo, int(ow), int(y0), int(y1 - y0), ay->d_start, ay->d_idx, ay->d_coef, d_dst); \
+        resize_h_kernel<C><<<gh, 256, 0, stream>>>(d_src, int(w), r_lo, rows_in, int(ow), ax->d_start, ax->d_tap, band); \
+        resize_v_kernel<C><<<gv, 256, 0, stream>>>(band, r_lo, int(ow), int(y0), int(y1 - y0), ay->d_start, ay->d_tap, d_dst); \
         break;
             VKT_RESIZE_CASE(1)
             VKT_RESIZE_CASE(2)
