@@ -71,6 +71,27 @@ int emul_chain_plan(const uint32_t *level_height, uint32_t num_levels, uint32_t 
     return int(split.sliced | (split.devices << 8));
 }
 
+// number of places where a tap list of ResizeAxis(in, out) steps back to a smaller input sample, or where the first /
+// last taps of consecutive outputs do (the vertical CUDA pass walks input rows in ascending order and relies on both)
+int emul_resize_axis_order_violations(int in, int out)
+{
+    vkt::ResizeAxis a;
+    a.build(in, out);
+    int bad = 0, prev_first = -1, prev_last = -1;
+    for(int o = 0; o < out; ++o)
+    {
+        const int t0 = a.start[size_t(o)], t1 = a.start[size_t(o) + 1];
+        for(int t = t0 + 1; t < t1; ++t) { bad += a.idx[size_t(t)] < a.idx[size_t(t) - 1]; }
+        if(t1 > t0)
+        {
+            bad += a.idx[size_t(t0)] < prev_first;
+            bad += a.idx[size_t(t1) - 1] < prev_last;
+            prev_first = a.idx[size_t(t0)], prev_last = a.idx[size_t(t1) - 1];
+        }
+    }
+    return bad;
+}
+
 // number of u8 values whose division-free decode (resize_decode_u8) differs from the reference's v / 255.0f
 int emul_resize_decode_mismatches()
 {

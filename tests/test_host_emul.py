@@ -66,6 +66,15 @@ def test_resize_decode_is_the_exact_quotient(emul):
     assert emul.lib.emul_resize_decode_mismatches() == 0
 
 
+def test_resize_tap_lists_ascend(emul):
+    """The vertical CUDA pass visits input rows in ascending order and feeds each to the outputs whose next tap it is: every
+    tap list must ascend (repeats allowed: clamped margins), for reductions, enlargements and the 1:1 Mitchell pass."""
+    pairs = [(n, n) for n in (4, 5, 8, 123, 124, 4096)] + [(n, (n // 2 + 3) & ~3) for n in (8, 12, 20, 84, 124, 520, 4096, 16384)]
+    pairs += [(123, 124), (81, 84), (4, 512), (4, 256), (1000, 3), (1000, 4), (17, 20), (300, 150), (7, 8), (50, 200), (50, 30), (33, 36)]
+    for i, o in pairs:
+        assert emul.lib.emul_resize_axis_order_violations(i, o) == 0, (i, o)
+
+
 RESIZE_SHAPES = [(64, 64, 64, 64, 4), (64, 64, 32, 32, 4), (123, 81, 124, 84, 4), (256, 128, 16, 8, 4), (60, 36, 60, 36, 3),
                  (4, 4, 512, 256, 4), (100, 52, 52, 28, 4), (124, 84, 64, 44, 4), (8, 4, 4, 4, 4), (4, 4, 4, 4, 4), (12, 20, 8, 12, 3),
                  (33, 7, 36, 8, 1), (50, 50, 200, 30, 2), (17, 300, 20, 150, 4), (640, 8, 320, 4, 4), (1024, 16, 512, 8, 4),
