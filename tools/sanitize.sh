@@ -1,0 +1,8 @@
+#!/bin/bash
+# compute-sanitizer over every kernel (under gpurun): bash tools/sanitize.sh <tag>
+T=${1:-x}; mkdir -p gpurun_out
+for tool in memcheck synccheck racecheck; do
+  echo "== $tool" >> gpurun_out/${T}_sanitizer.txt
+  timeout 600 compute-sanitizer --tool $tool python tools/sanitize_target.py 2>&1 | tail -3 >> gpurun_out/${T}_sanitizer.txt
+done
+cat gpurun_out/${T}_sanitizer.txt

@@ -178,6 +178,7 @@ VKT_FN bool warp_any(bool p) { return __ballot_sync(__activemask(), p) != 0u; }
 constexpr uint32_t kWarpLanes = 32;
 VKT_FN uint32_t warp_lane() { return threadIdx.x & 31u; }
 VKT_FN uint32_t warp_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+VKT_FN void warp_sync() { __syncwarp(); }
 VKT_FN uint64_t warp_min_u64(uint64_t v)
 {
 #pragma unroll
@@ -207,6 +208,7 @@ VKT_FN bool warp_any(bool p) { return p; }
 constexpr uint32_t kWarpLanes = 1;// host emulation: a "warp" is one lane
 VKT_FN uint32_t warp_lane() { return 0; }
 VKT_FN uint32_t warp_ballot(bool p) { return p ? 1u : 0u; }
+VKT_FN void warp_sync() {}
 VKT_FN uint64_t warp_min_u64(uint64_t v) { return v; }
 VKT_FN uint32_t dp4a_u8(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -1415,6 +1417,7 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
 #endif
     if(total_partitions > kUniformIters)
     {
+        warp_sync();// lanes are about to read each other's columns (written by their owners in prepare_lane)
         running = running && (best_err > 0);
         uint32_t pending = warp_ballot(running);
         const uint32_t lane = warp_lane();
