@@ -1580,9 +1580,14 @@ VKT_FN uint64_t two_subset_cells(const Bc7Tables &T, const Bc7KernelParams &P, L
     Cell c[2];
     const float mw = (MODE == 1) ? P.mode1_w : P.mode7_w;
     uint64_t trial = 0;
+    // Every lane fits its LARGER subset first: the warp's texel loops then run max(8..15) + max(1..8) trips instead of twice
+    // max(1..15).  The two fits are independent and their errors only add, so the order changes neither the result nor
+    // the outcome of the early exit below (weigh() is monotone: a partial sum above best_err means the total is too).
+    const int second = (n1 > n0) ? 0 : 1;// subset fitted in the second pass
 #pragma unroll 1
-    for(int s = 0; s < 2; ++s)
+    for(int pass = 0; pass < 2; ++pass)
     {
+        const int s = pass ? second : 1 - second;
         const CellRef cell = {s ? perm1 : perm0, s ? n1 : n0};
         Cell r;
         trial += compress_cell<MODE, ALPHA, PERC, KEY28, UBER, STRIDE>(T, P, L, cell, r);
