@@ -26,6 +26,8 @@ if(VIERKANT_BCN_CUDA)
     list(FILTER _vkt_sources EXCLUDE REGEX "texture_block_compression\\.cpp$")
     set_target_properties(vierkant PROPERTIES SOURCES "${_vkt_sources}")
     target_sources(vierkant PRIVATE ${VIERKANT_BCN_CUDA_DIR}/integration/texture_block_compression_cuda.cpp)
+    # texture_block_compression_batch.hpp: the optional several-textures-per-call overload (for model::compress_textures)
+    target_include_directories(vierkant PUBLIC ${VIERKANT_BCN_CUDA_DIR}/integration)
     target_link_libraries(vierkant PUBLIC vierkant_bcn_cuda)
     target_compile_definitions(vierkant PUBLIC VIERKANT_BCN_CUDA=1)
 endif()
