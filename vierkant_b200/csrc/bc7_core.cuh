@@ -8,10 +8,12 @@
 //     (SURVEY.md F12), so it runs once per lane with zero redundancy.
 //   * per-lane state lives in a shared-memory column (texels + their YCbCr, hoisted once per block), conflict-free.
 //   * partition estimator: the candidate list is walked warp-uniformly (every lane scores the same partition in the
-//     same iteration; the membership mask comes from __constant__ memory and stays in uniform registers, so the
-//     16-texel loops are fully unrolled with uniform branches) and a warp ballot skips candidates no lane of the batch
-//     still needs.  Bounding boxes use 16x2 SIMD min/max (VIMNMX.U16x2), palettes are built two channels per IMAD,
-//     projections are IDP.4A dot products, the selected palette entry is a packed RGBA word.
+//     same iteration; per subset a rolled loop over that subset's texel PAIRS, listed per partition in __constant__
+//     memory) and a warp ballot skips candidates no lane of the batch still needs; for the filterbank phase the CTA
+//     regroups its blocks by key partition so that the lanes of a warp need the same candidates.  Bounding boxes use
+//     16x2 SIMD min/max (VIMNMX3.U16x2), palettes are built two channels per IMAD, projections are IDP.4A dot products,
+//     the selected palette entry is a packed RGBA word.  Opaque blocks run the estimator before anything else.
+//   * two-subset modes fit the larger subset of every lane first (warp loop trips: max(8..15) + max(1..8)).
 //   * selector search: palette in registers in YCbCr, unrolled over the N entries; error and selector are fused in
 //     one key (err * 16 + j) so the argmin is a single VIMNMX per candidate (first minimum wins, as the reference).
 //   * every colour-cell search has ONE call site for least-squares + quantise + evaluate (a small stage machine walks
