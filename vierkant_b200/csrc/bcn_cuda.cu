@@ -69,7 +69,11 @@ __device__ __forceinline__ void load_block_texels(const uint8_t *__restrict__ im
 #ifndef VKT_BC7_CTAS_ALPHA
 #define VKT_BC7_CTAS_ALPHA 2
 #endif
-constexpr int kBc7Threads = VKT_BC7_THREADS;
+#ifndef VKT_BC7_THREADS_ALPHA
+#define VKT_BC7_THREADS_ALPHA 256
+#endif
+constexpr int kBc7Threads = VKT_BC7_THREADS, kBc7ThreadsAlpha = VKT_BC7_THREADS_ALPHA;
+__host__ __device__ constexpr int bc7_threads(bool alpha) { return alpha ? kBc7ThreadsAlpha : kBc7Threads; }
 // Opaque blocks: 3 CTAs/SM = 3 x (64 KB lane columns + tables) of shared memory at <= 80 registers per thread.
 // Alpha blocks carry a fourth channel through every stage: 2 CTAs/SM at <= 128 registers (no spills) is faster.
 constexpr int kBc7CtasPerSm = VKT_BC7_CTAS, kBc7CtasPerSmAlpha = VKT_BC7_CTAS_ALPHA;
@@ -192,12 +196,16 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm
     if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
-constexpr size_t bc7_smem_bytes(bool alpha) { return bc7_smem_table_bytes(alpha) + size_t(kBc7Threads) * 16 * sizeof(Texel) + sizeof(CtaScratch<kBc7Threads>); }
+constexpr size_t bc7_smem_bytes(bool alpha)
+{
+    return bc7_smem_table_bytes(alpha) + size_t(bc7_threads(alpha)) * 16 * sizeof(Texel) + (alpha ? sizeof(CtaScratch<kBc7ThreadsAlpha>) : sizeof(CtaScratch<kBc7Threads>));
+}
 
 template<bool PERC, bool KEY28, bool ALPHA, bool UBER>
 static cudaError_t bc7_kernel_attribute()
 {
-    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, kBc7Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bc7_smem_bytes(ALPHA)));
+    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, bc7_threads(ALPHA)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(bc7_smem_bytes(ALPHA)));
 }
 // > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
 static cudaError_t bc7_kernel_attributes()
@@ -389,25 +397,25 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
         if(total == 0) { continue; }
         if(total > 0xFFFFFFF0ull) { return fail(ctx, VKT_BCN_ERR_INVALID, "more than 2^32 blocks in one launch"); }
         B.total_blocks = uint32_t(total);
-        const uint32_t grid = (B.total_blocks + kBc7Threads - 1) / kBc7Threads;
         auto encode = [&](bool alpha, const uint32_t *list, const uint32_t *cnt) {
-            auto go = [&](auto kernel) { kernel<<<grid, kBc7Threads, bc7_smem_bytes(alpha), stream>>>(B, kp, s->d_tables, list, cnt); };
+            const uint32_t nt = uint32_t(bc7_threads(alpha)), grid = (B.total_blocks + nt - 1) / nt;
+            auto go = [&](auto kernel) { kernel<<<grid, nt, bc7_smem_bytes(alpha), stream>>>(B, kp, s->d_tables, list, cnt); };
             // uber-free kernels exist for the 28-bit-key variants (every sane weight set); the wide-error ones always carry the stages
             const int sel = ((kp.uber_level == 0 && kp.key28) ? 8 : 0) | (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
             switch(sel)
             {
-                case 15: go(bc7_encode_kernel<true, true, true, false, kBc7Threads>); break;
+                case 15: go(bc7_encode_kernel<true, true, true, false, kBc7ThreadsAlpha>); break;
                 case 14: go(bc7_encode_kernel<true, true, false, false, kBc7Threads>); break;
 #ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY// (tuning builds compile the two default-parameter kernels only)
-                case 11: go(bc7_encode_kernel<false, true, true, false, kBc7Threads>); break;
+                case 11: go(bc7_encode_kernel<false, true, true, false, kBc7ThreadsAlpha>); break;
                 case 10: go(bc7_encode_kernel<false, true, false, false, kBc7Threads>); break;
-                case 7: go(bc7_encode_kernel<true, true, true, true, kBc7Threads>); break;
+                case 7: go(bc7_encode_kernel<true, true, true, true, kBc7ThreadsAlpha>); break;
                 case 6: go(bc7_encode_kernel<true, true, false, true, kBc7Threads>); break;
-                case 5: go(bc7_encode_kernel<true, false, true, true, kBc7Threads>); break;
+                case 5: go(bc7_encode_kernel<true, false, true, true, kBc7ThreadsAlpha>); break;
                 case 4: go(bc7_encode_kernel<true, false, false, true, kBc7Threads>); break;
-                case 3: go(bc7_encode_kernel<false, true, true, true, kBc7Threads>); break;
+                case 3: go(bc7_encode_kernel<false, true, true, true, kBc7ThreadsAlpha>); break;
                 case 2: go(bc7_encode_kernel<false, true, false, true, kBc7Threads>); break;
-                case 1: go(bc7_encode_kernel<false, false, true, true, kBc7Threads>); break;
+                case 1: go(bc7_encode_kernel<false, false, true, true, kBc7ThreadsAlpha>); break;
                 default: go(bc7_encode_kernel<false, false, false, true, kBc7Threads>); break;
 #else
                 default: break;
