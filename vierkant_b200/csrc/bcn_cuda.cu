@@ -76,7 +76,11 @@ constexpr int kBc7Threads = VKT_BC7_THREADS, kBc7ThreadsAlpha = VKT_BC7_THREADS_
 __host__ __device__ constexpr int bc7_threads(bool alpha) { return alpha ? kBc7ThreadsAlpha : kBc7Threads; }
 // Opaque blocks: 3 CTAs/SM = 3 x (64 KB lane columns + tables) of shared memory at <= 80 registers per thread.
 // Alpha blocks carry a fourth channel through every stage: 2 CTAs/SM at <= 128 registers (no spills) is faster.
-constexpr int kBc7CtasPerSm = VKT_BC7_CTAS, kBc7CtasPerSmAlpha = VKT_BC7_CTAS_ALPHA;
+// So are the opaque kernels that carry the uber-level stages (selector-search dominated: +2.4 % at uber level 4).
+#ifndef VKT_BC7_CTAS_UBER
+#define VKT_BC7_CTAS_UBER 2
+#endif
+constexpr int kBc7CtasPerSm = VKT_BC7_CTAS, kBc7CtasPerSmAlpha = VKT_BC7_CTAS_ALPHA, kBc7CtasPerSmUber = VKT_BC7_CTAS_UBER;
 
 // Up to 16 images (the levels of a mip chain, the textures of a material, or row slices of them) are encoded by ONE
 // launch: the block index space of the launch is the concatenation of the images' block arrays.  A tail of tiny mip
@@ -165,7 +169,7 @@ static_assert(offsetof(Bc7Tables, opt7) % 16 == 0, "table prefix is copied as ui
 // One lane == one block of the work list (list == nullptr: every block of the launch, in order).
 // UBER == false: the search without the uber-level stages (launched when uber_level == 0).
 template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int NT>
-__global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : kBc7CtasPerSm)
+__global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : (UBER ? kBc7CtasPerSmUber : kBc7CtasPerSm))
         bc7_encode_kernel(const __grid_constant__ Bc7Batch B, const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables,
                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ count)
 {
