@@ -30,7 +30,7 @@ extern "C" {
 
 #define VKT_BCN_OK 0
 #define VKT_BCN_ERR_INVALID (-1)     /* bad argument (null pointer, size not a multiple of 4, comps not 3/4, ...) */
-#define VKT_BCN_ERR_UNSUPPORTED (-2) /* a parameter combination this encoder deliberately does not implement */
+#define VKT_BCN_ERR_UNSUPPORTED (-2) /* reserved (no parameter combination is refused as unsupported any more) */
 #define VKT_BCN_ERR_CUDA (-3)        /* CUDA runtime failure, see vkt_bcn_cuda_last_error */
 #define VKT_BCN_ERR_NO_DEVICE (-4)   /* no CUDA device / driver: the library has no CPU path */
 #define VKT_BCN_ERR_OOM (-5)
@@ -45,9 +45,13 @@ typedef struct vkt_bcn_ctx vkt_bcn_ctx;
  * struct across the ABI (it contains bools and padding); vkt_bc7_params_init() = bc7enc_compress_block_params_init()
  * (bc7enc.h:95-113), which is what vierkant uses (texture_block_compression.cpp:73-74).
  *
- * Deliberately unsupported (VKT_BCN_ERR_UNSUPPORTED): force_selectors and quant_mode6_endpoints (only driven by
- * bc7enc_rdo's RDO post-processor, which vierkant does not compile, src/CMakeLists.txt:11) and
- * low_frequency_partition_weight != 1.0 (it makes the estimator's work-saving early-outs observable). */
+ * Every field is honoured.  force_selectors / selectors, quant_mode6_endpoints and low_frequency_partition_weight != 1.0
+ * (only driven by bc7enc_rdo's RDO post-processor, which vierkant does not compile, src/CMakeLists.txt:11) run on a
+ * separate, slower kernel variant that keeps the estimator's early-outs (bc7enc.cpp:1536,1810), which such a weight makes
+ * observable.  VKT_BCN_ERR_INVALID: uber_level > 4; a mode_mask without an opaque (6 | 1) or an alpha (5 | 6 | 7) mode (the
+ * reference asserts); with force_selectors, a selector that does not exist in the palette of every enabled mode (16 / 8 / 4
+ * entries for mode 6 / 1 / 5 and 7 -- the reference would read an uninitialised colour); a low-frequency weight that is
+ * negative, above 65536 or NaN (the reference's float -> uint64 conversion is undefined there). */
 typedef struct vkt_bc7_params
 {
     uint32_t mode_mask;

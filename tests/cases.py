@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import numpy as np
 
-# every knob of bc7enc_compress_block_params the C ABI accepts (SURVEY.md F10, App. E "stage-wise oracles")
+# the knobs of bc7enc_compress_block_params vierkant could reach (SURVEY.md F10, App. E "stage-wise oracles")
 PARAM_CASES = {
     "defaults": dict(),
     "filterbank_off": dict(mode17_partition_estimation_filterbank=0),
@@ -29,11 +29,32 @@ PARAM_CASES = {
     "big_weights": dict(weights=[800, 400, 100, 200]),
     "big_weights_linear": dict(perceptual=0, weights=[9000, 7000, 5000, 6000]),
 }
-# accepted by the oracles only (the C ABI returns VKT_BCN_ERR_UNSUPPORTED)
-ORACLE_ONLY_CASES = {
+# the three knobs bc7enc_rdo's RDO post-processor drives (bc7enc.cpp:697, :838/:885, :1819); vierkant never sets them.
+# Served by the extended kernel variant (kKvExt), whose estimator keeps the reference's early-outs.
+RDO_CASES = {
     "low_freq_weight": dict(low_frequency_partition_weight=0.75),
     "quant_mode6": dict(quant_mode6_endpoints=1),
     "force_selectors": dict(force_selectors=1, selectors=list(range(16)), mode_mask=1 << 6),
+    "low_freq_weight_fb_off": dict(low_frequency_partition_weight=0.5, mode17_partition_estimation_filterbank=0),
+    "low_freq_weight_up": dict(low_frequency_partition_weight=1.5),
+    "low_freq_weight_zero": dict(low_frequency_partition_weight=0.0),
+    "low_freq_weight_linear": dict(low_frequency_partition_weight=0.6, perceptual=0, weights=[1, 1, 1, 1]),
+    "quant_mode6_uber2": dict(quant_mode6_endpoints=1, uber_level=2),
+    "quant_mode6_linear": dict(quant_mode6_endpoints=1, perceptual=0, weights=[1, 1, 1, 1]),
+    "force_selectors_all_modes": dict(force_selectors=1, selectors=[0, 1, 2, 3, 3, 2, 1, 0, 1, 3, 0, 2, 2, 0, 3, 1]),
+    "force_selectors_opaque_modes": dict(force_selectors=1, selectors=[7, 6, 5, 4, 3, 2, 1, 0, 0, 2, 4, 6, 1, 3, 5, 7],
+                                         mode_mask=(1 << 6) | (1 << 1)),
+    "rdo_all_three": dict(force_selectors=1, selectors=[3, 3, 2, 2, 1, 1, 0, 0, 0, 1, 2, 3, 3, 2, 1, 0], quant_mode6_endpoints=1,
+                          low_frequency_partition_weight=0.8, uber_level=1),
+}
+# parameter sets the C ABI must reject (VKT_BCN_ERR_INVALID)
+INVALID_CASES = {
+    "selector_beyond_mode1_palette": dict(force_selectors=1, selectors=[8] + [0] * 15, mode_mask=(1 << 6) | (1 << 1)),
+    "selector_beyond_mode5_palette": dict(force_selectors=1, selectors=[4] + [0] * 15),
+    "negative_low_freq_weight": dict(low_frequency_partition_weight=-0.5),
+    "nan_low_freq_weight": dict(low_frequency_partition_weight=float("nan")),
+    "uber_level_5": dict(uber_level=5),
+    "no_opaque_mode": dict(mode_mask=1 << 5),
 }
 
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(HERE))
 
-from cases import ORACLE_ONLY_CASES, PARAM_CASES, edge_tiles  # noqa: E402
+from cases import RDO_CASES, PARAM_CASES, edge_tiles  # noqa: E402
 from oracle.pyoracle import RefOracle, build, default_params  # noqa: E402
 from vierkant_b200 import synth  # noqa: E402
 
@@ -28,7 +28,7 @@ def main():
     tiles = np.concatenate([edge_tiles(7, 16), synth.to_blocks(synth.make_texture(32, 32, 0)),
                             synth.to_blocks(synth.make_texture(32, 32, 1))])
     out = {"tiles": tiles}
-    for name, kw in {**PARAM_CASES, **ORACLE_ONLY_CASES}.items():
+    for name, kw in {**PARAM_CASES, **RDO_CASES}.items():
         out["blocks_" + name] = ref.encode_blocks(tiles, default_params(**kw), threads=4)
     out["bc5_blocks"] = ref.encode_bc5_blocks(tiles)
     out["decoded_defaults"] = ref.unpack_blocks(out["blocks_defaults"])

@@ -15,11 +15,11 @@
 #include "../../vierkant_b200/csrc/resize_axis.h"
 
 // the uber-free instantiation whenever the parameters allow it, as the CUDA dispatch does
-template<bool PERC, bool KEY28, bool ALPHA>
+template<bool PERC, int KV, bool ALPHA>
 static void enc(const vkt::Bc7Tables &tables, const vkt::Bc7KernelParams &kp, vkt::Lane<1> lane, uint32_t blk[4])
 {
-    if(kp.uber_level == 0) { vkt::encode_block<PERC, KEY28, ALPHA, false, 1>(tables, kp, lane, blk); }
-    else { vkt::encode_block<PERC, KEY28, ALPHA, true, 1>(tables, kp, lane, blk); }
+    if(kp.uber_level == 0 && KV == vkt::kKvKey28) { vkt::encode_block<PERC, KV, ALPHA, false, 1>(tables, kp, lane, blk); }
+    else { vkt::encode_block<PERC, KV, ALPHA, true, 1>(tables, kp, lane, blk); }
 }
 
 extern "C" {
@@ -138,6 +138,10 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
     }
     int rc = vkt::bc7_prepare_params(params, &kp);
     if(rc) { return rc; }
+    static uint8_t m6_reduced[vkt::kBc7M6ReducedBytes];
+    static bool once6 = (vkt::bc7_m6_reduced_build(m6_reduced), true);
+    (void) once6;
+    kp.m6_reduced = m6_reduced;
     const bool perceptual = params->perceptual != 0;
     auto work = [&](uint64_t b0, uint64_t b1) {
         vkt::Texel column[16];
@@ -149,9 +153,14 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
             uint32_t raw[16];
             memcpy(raw, px + 64 * b, 64);
             const bool alpha = vkt::block_has_alpha(kp, raw);
-            const int sel = (perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            int sel = (perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            if(kp.ext) { sel = 8 | (perceptual ? 2 : 0) | (alpha ? 1 : 0); }// the extended variant, as the CUDA dispatch picks it
             switch(sel)
             {
+                case 11: enc<true, vkt::kKvExt, true>(tables, kp, lane, blk); break;
+                case 10: enc<true, vkt::kKvExt, false>(tables, kp, lane, blk); break;
+                case 9: enc<false, vkt::kKvExt, true>(tables, kp, lane, blk); break;
+                case 8: enc<false, vkt::kKvExt, false>(tables, kp, lane, blk); break;
                 case 7: enc<true, true, true>(tables, kp, lane, blk); break;
                 case 6: enc<true, true, false>(tables, kp, lane, blk); break;
                 case 5: enc<true, false, true>(tables, kp, lane, blk); break;

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import ORACLE_ONLY_CASES, PARAM_CASES, edge_tiles, tiles_to_image
+from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles, tiles_to_image
 from oracle.pyoracle import default_params as oracle_params
 from vierkant_b200 import capi, synth
 
@@ -22,24 +22,27 @@ def golden():
     return np.load(os.path.join(GOLD, "bc7_blocks.npz"))
 
 
-@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+ALL_CASES = {**PARAM_CASES, **RDO_CASES}
+
+
+@pytest.mark.parametrize("case", sorted(ALL_CASES))
 def test_golden_vectors(ctx, golden, case):
-    """Committed reference outputs (tests/golden/make_golden.py) for every supported parameter case."""
+    """Committed reference outputs (tests/golden/make_golden.py) for every parameter case."""
     tiles = golden["tiles"]
     n = tiles.shape[0]
     bx = 8
     pad = (-n) % bx
     t = np.concatenate([tiles, np.repeat(tiles[-1:], pad, axis=0)]) if pad else tiles
-    got = ctx.encode_bc7(tiles_to_image(t, bx), gpu_params(PARAM_CASES[case]))[:n]
+    got = ctx.encode_bc7(tiles_to_image(t, bx), gpu_params(ALL_CASES[case]))[:n]
     assert np.array_equal(got, golden["blocks_" + case])
 
 
-@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+@pytest.mark.parametrize("case", sorted(ALL_CASES))
 @pytest.mark.parametrize("kind", [0, 1])
 def test_synthetic_texture_matches_oracle(ctx, port_oracle, case, kind):
     img = synth.make_texture(256, 256, kind)
-    want = port_oracle.encode_blocks(synth.to_blocks(img), oracle_params(**PARAM_CASES[case]), threads=os.cpu_count() or 1)
-    got = ctx.encode_bc7(img, gpu_params(PARAM_CASES[case]))
+    want = port_oracle.encode_blocks(synth.to_blocks(img), oracle_params(**ALL_CASES[case]), threads=os.cpu_count() or 1)
+    got = ctx.encode_bc7(img, gpu_params(ALL_CASES[case]))
     mism = int((got != want).any(axis=1).sum())
     assert mism == 0, f"{mism} / {len(want)} blocks differ"
 
@@ -88,11 +91,21 @@ def test_batch_of_levels(ctx, port_oracle):
         assert np.array_equal(o, port_oracle.encode_blocks(synth.to_blocks(i)))
 
 
-@pytest.mark.parametrize("name", sorted(ORACLE_ONLY_CASES))
-def test_unsupported_parameters_fail_loudly(ctx, name):
+@pytest.mark.parametrize("name", sorted(INVALID_CASES))
+def test_invalid_parameters_fail_loudly(ctx, name):
     with pytest.raises(capi.BcnError) as e:
-        ctx.encode_bc7(synth.make_texture(8, 8, 0), gpu_params(ORACLE_ONLY_CASES[name]))
-    assert e.value.code == capi.ERR_UNSUPPORTED
+        ctx.encode_bc7(synth.make_texture(8, 8, 0), gpu_params(INVALID_CASES[name]))
+    assert e.value.code == capi.ERR_INVALID
+
+
+def test_rdo_knobs_match_reference_build(ctx, ref_oracle):
+    """Forced selectors, reduced mode-6 quantisation and the low-frequency partition weight against the unmodified reference
+    itself (oracle/_ref), on edge-case tiles."""
+    tiles = edge_tiles(91, 96)
+    img = tiles_to_image(tiles, 32)
+    for name in sorted(RDO_CASES):
+        want = ref_oracle.encode_blocks(tiles, oracle_params(**RDO_CASES[name]), threads=os.cpu_count() or 1)
+        assert np.array_equal(ctx.encode_bc7(img, gpu_params(RDO_CASES[name])), want), name
 
 
 @pytest.mark.parametrize("w,h,c", [(6, 4, 4), (4, 4, 2), (0, 4, 4)])

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import PARAM_CASES, edge_tiles
+from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles
 from oracle.pyoracle import Bc7Params, default_params
 from vierkant_b200 import synth
 
@@ -46,19 +46,33 @@ def test_uber_selector_maps_match_reference_expression(emul):
     assert emul.lib.emul_uber_map_mismatches() == 0
 
 
-@pytest.mark.parametrize("case", sorted(PARAM_CASES))
+ALL_CASES = {**PARAM_CASES, **RDO_CASES}
+
+
+@pytest.mark.parametrize("case", sorted(ALL_CASES))
 def test_device_logic_matches_oracle(emul, port_oracle, case):
     tiles = np.concatenate([edge_tiles(21, 30), synth.to_blocks(synth.make_texture(96, 96, 1, seed=5))])
-    p = default_params(**PARAM_CASES[case])
+    p = default_params(**ALL_CASES[case])
     rc, got = emul(tiles, p)
     assert rc == 0
     assert np.array_equal(got, port_oracle.encode_blocks(tiles, p, threads=4))
 
 
-@pytest.mark.parametrize("kw", [dict(force_selectors=1), dict(quant_mode6_endpoints=1), dict(low_frequency_partition_weight=0.5)])
-def test_unsupported_knobs_are_rejected(emul, kw):
-    rc, _ = emul(edge_tiles(1, 1), default_params(**kw))
-    assert rc == -2
+@pytest.mark.parametrize("case", sorted(RDO_CASES))
+def test_rdo_knobs_match_reference_build(emul, ref_oracle, case):
+    """The extended variant (forced selectors, reduced mode-6 quantisation, low-frequency partition weight) against the
+    unmodified reference itself."""
+    tiles = np.concatenate([edge_tiles(33, 24), synth.to_blocks(synth.make_texture(64, 64, 0, seed=8))])
+    p = default_params(**RDO_CASES[case])
+    rc, got = emul(tiles, p)
+    assert rc == 0
+    assert np.array_equal(got, ref_oracle.encode_blocks(tiles, p, threads=4))
+
+
+@pytest.mark.parametrize("case", sorted(INVALID_CASES))
+def test_invalid_parameters_are_rejected(emul, case):
+    rc, _ = emul(edge_tiles(1, 1), default_params(**INVALID_CASES[case]))
+    assert rc == -1
 
 
 def test_resize_decode_is_the_exact_quotient(emul):

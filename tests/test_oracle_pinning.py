@@ -6,12 +6,12 @@ import os
 import numpy as np
 import pytest
 
-from cases import ORACLE_ONLY_CASES, PARAM_CASES, edge_tiles
+from cases import RDO_CASES, PARAM_CASES, edge_tiles
 from oracle.pyoracle import default_params
 from vierkant_b200 import synth
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-ALL_CASES = {**PARAM_CASES, **ORACLE_ONLY_CASES}
+ALL_CASES = {**PARAM_CASES, **RDO_CASES}
 
 
 @pytest.fixture(scope="module")

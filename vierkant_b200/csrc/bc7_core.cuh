@@ -172,6 +172,10 @@ VKT_FN float fsqrt(float a) { return __fsqrt_rn(a); }
 VKT_FN int f2i(float a) { return __float2int_rz(a); }// operands are always saturated first (bc7enc.cpp:871)
 VKT_FN float u64_to_f(uint64_t a) { return __ull2float_rn(a); }
 VKT_FN uint64_t f_to_u64(float a) { return __float2ull_rz(a); }
+VKT_FN double u64_to_d(uint64_t a) { return __ull2double_rn(a); }
+VKT_FN uint64_t d_to_u64(double a) { return __double2ull_rz(a); }
+VKT_FN double dmul(double a, double b) { return __dmul_rn(a, b); }
+VKT_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
 VKT_FN int popc32(uint32_t m) { return __popc(m); }
 VKT_FN int ctz32(uint32_t m) { return __ffs(m) - 1; }
 // true if any lane of the currently converged group of the warp holds `p`
@@ -204,6 +208,10 @@ VKT_FN float fsqrt(float a) { return sqrtf(a); }
 VKT_FN int f2i(float a) { return (int) a; }
 VKT_FN float u64_to_f(uint64_t a) { return (float) a; }
 VKT_FN uint64_t f_to_u64(float a) { return (uint64_t) a; }
+VKT_FN double u64_to_d(uint64_t a) { return (double) a; }
+VKT_FN uint64_t d_to_u64(double a) { return (uint64_t) a; }
+VKT_FN double dmul(double a, double b) { return a * b; }
+VKT_FN double dadd(double a, double b) { return a + b; }
 VKT_FN int popc32(uint32_t m) { return __builtin_popcount(m); }
 VKT_FN int ctz32(uint32_t m) { return __builtin_ctz(m); }
 VKT_FN bool warp_any(bool p) { return p; }
@@ -262,6 +270,8 @@ VKT_FN int iabs(int a) { return a < 0 ? -a : a; }
 
 // the (uint64)(err * weight + .5f) round trip, bc7enc.cpp:2167,2184,2234,2239,2326,2377,2382
 VKT_FN uint64_t weigh(uint64_t err, float w) { return f_to_u64(fadd(fmul(u64_to_f(err), w), .5f)); }
+// (uint64_t)((double)err * w + .5f), bc7enc.cpp:1819: the float weight and the .5f are promoted, product and sum in double
+VKT_FN uint64_t weigh_d(uint64_t err, float w) { return d_to_u64(dadd(dmul(u64_to_d(err), (double) w), 0.5)); }
 
 // byte c of a packed RGBA8 word (c is a compile-time constant at every call site): one PRMT
 VKT_FN uint32_t byte_of(uint32_t v, int c) { return prmt(v, 0u, 0x4440u | (uint32_t) c); }
@@ -290,7 +300,24 @@ struct Bc7KernelParams
                     // compiler otherwise multiplies by w and shifts every key)
     float pbit1_weight;
     float mode1_w, mode5_w, mode6_w, mode7_w;
+    // The three knobs bc7enc_rdo's RDO post-processor drives; only read by the extended kernel variant (KV == kKvExt),
+    // which the host launches when one of them departs from its default.
+    uint32_t ext;              // 1 if any of them is set: launch the extended variant
+    uint32_t force_selectors;  // bc7enc.cpp:697
+    uint32_t quant_mode6;      // bc7enc.cpp:838,885
+    uint64_t forced_sel;       // m_selectors[16], one nibble per cell element
+    float low_freq_weight;     // bc7enc.cpp:1819
+    const uint8_t *m6_reduced; // g_mode6_reduced_quant[2048][2] (bc7enc.cpp:188-211) in device memory, [value][p]
 };
+
+// Kernel variant (template parameter KV of everything below):
+//   kKvWide  per-texel errors may need more than 28 bits: 64-bit (error, selector) bookkeeping
+//   kKvKey28 every per-texel error is provably < 2^28 (host-checked from the weights): error and selector share one
+//            32-bit argmin key -- the variant every sane weight set runs
+//   kKvExt   kKvWide plus forced selectors, reduced mode-6 endpoint quantisation and the low-frequency partition weight;
+//            its estimator keeps the reference's work-saving early-outs, which that weight makes observable
+// (bool arguments still select the first two: false -> kKvWide, true -> kKvKey28)
+constexpr int kKvWide = 0, kKvKey28 = 1, kKvExt = 2;
 
 // One texel of the block with its hoisted YCbCr (bc7enc.cpp:511-516): 16 bytes, fetched with a single 128-bit shared load.
 struct alignas(16) Texel
@@ -485,12 +512,13 @@ VKT_FN uint64_t solid_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<ST
 
 // ---------------------------------------------------------------------------------------------------- evaluate_solution
 // bc7enc.cpp:645-831.  lo/hi are quantised endpoints (no p-bits), pbits bit0/bit1.  Updates `best` on strict improvement.
-template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE>
 VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uint32_t lo, uint32_t hi, uint32_t pbits, Cell &best)
 {
     typedef ModeTraits<MODE> M;
     constexpr int N = M::N;
     constexpr int NBITS = M::comp_bits + (M::pbits ? 1 : 0);
+    constexpr bool KEY28 = (KV == kKvKey28);
     uint32_t qlo = lo, qhi = hi;
     if(M::pbits)
     {
@@ -517,7 +545,20 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
     }
 
     uint64_t total = 0, sel = 0;
-    if(PERC)
+    if((KV == kKvExt) && P.force_selectors)
+    {
+        // bc7enc.cpp:697-712: element k of the cell takes m_selectors[k] (the cell's own numbering, also in the two-subset modes)
+        for(int k = 0; k < cell.n; ++k)
+        {
+            const uint32_t s = (uint32_t) (P.forced_sel >> (4 * k)) & 15u;// < N (host-checked against the enabled modes)
+            uint32_t c = pal[0];
+#pragma unroll
+            for(int j = 1; j < N; ++j) { c = (s == (uint32_t) j) ? pal[j] : c; }
+            total += dist_px<PERC, ALPHA>(c, L.px(cell.at(k)), P.w);
+            sel |= (uint64_t) s << (4 * k);
+        }
+    }
+    else if(PERC)
     {
         int pl[N], pcr[N], pcb[N], pa[N];
 #pragma unroll
@@ -634,7 +675,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
 
 // ---------------------------------------------------------------------------------------------------- find_optimal_solution
 // bc7enc.cpp:868-1099 (+ fixDegenerateEndpoints :833-866).  xl/xh are float endpoints in [0,1] (saturated here).
-template<int MODE, bool ALPHA, bool PERC, bool KEY28, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE>
 VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, const float xl_in[4], const float xh_in[4],
                     Cell &best)
 {
@@ -653,9 +694,22 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         {
             // independent p-bits (modes 6, 7), bc7enc.cpp:901-973
             float best0 = 1e+9f, best1 = 1e+9f;
+            const bool reduced = (KV == kKvExt) && (M::comp_bits == 7) && P.quant_mode6;
+            if(reduced)
+            {
+                // bc7enc.cpp:885-899: 64 endpoint levels from a table, low endpoint with p = 0, high endpoint with p = 1
+                bpb = 2u;
+#pragma unroll
+                for(int c = 0; c < 4; ++c)
+                {
+                    blo |= (uint32_t) P.m6_reduced[f2i(fadd(fmul(xl[c], 2047.0f), .5f)) * 2 + 0] << (8 * c);
+                    bhi |= (uint32_t) P.m6_reduced[f2i(fadd(fmul(xh[c], 2047.0f), .5f)) * 2 + 1] << (8 * c);
+                }
+            }
 #pragma unroll
             for(int p = 0; p < 2; ++p)
             {
+                if(reduced) { break; }
                 uint32_t qlo = 0, qhi = 0;
                 float e0 = 0.0f, e1 = 0.0f;
 #pragma unroll
@@ -768,9 +822,9 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
             }
         }
 
-        if(MODE == 1)
+        if((MODE == 1) || ((KV == kKvExt) && (MODE == 6) && P.quant_mode6))
         {
-            // fixDegenerateEndpoints, bc7enc.cpp:833-866, iscale = iscalep >> 1 = 63
+            // fixDegenerateEndpoints, bc7enc.cpp:833-866, iscale = iscalep >> 1 = 63 (mode 1) / 127 (mode 6, reduced quantisation)
             constexpr uint32_t iscale = (uint32_t) (iscalep >> 1);
 #pragma unroll
             for(int c = 0; c < 3; ++c)
@@ -795,7 +849,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi) || ((bpb & 3u) != (best.pbits & 3u)))
         {
-            evaluate<MODE, ALPHA, PERC, KEY28, STRIDE>(P, L, cell, blo, bhi, bpb, best);
+            evaluate<MODE, ALPHA, PERC, KV, STRIDE>(P, L, cell, blo, bhi, bpb, best);
         }
     }
     else
@@ -813,7 +867,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi))
         {
-            evaluate<MODE, ALPHA, PERC, KEY28, STRIDE>(P, L, cell, blo, bhi, best.pbits, best);
+            evaluate<MODE, ALPHA, PERC, KV, STRIDE>(P, L, cell, blo, bhi, best.pbits, best);
         }
     }
     return best.err;
@@ -880,7 +934,7 @@ VKT_FN void least_squares(const Bc7Tables &T, Lane<STRIDE> L, CellRef cell, uint
 // bc7enc.cpp:1101-1441
 // UBER == false compiles the search without the uber-level stages (P.uber_level must be 0): the default-parameter
 // kernels then carry only the two stages they execute, which keeps their working set of instructions small.
-template<int MODE, bool ALPHA, bool PERC, bool KEY28, bool UBER, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, int KV, bool UBER, int STRIDE>
 VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, Cell &out)
 {
     typedef ModeTraits<MODE> M;
@@ -1095,7 +1149,7 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             }
             least_squares<MODE, ALPHA, STRIDE>(T, L, cell, trial, xl, xh);
         }
-        if(!fit<MODE, ALPHA, PERC, KEY28, STRIDE>(T, P, L, cell, xl, xh, out)) { return 0; }
+        if(!fit<MODE, ALPHA, PERC, KV, STRIDE>(T, P, L, cell, xl, xh, out)) { return 0; }
 
         // advance
         if(stage == 0)
@@ -1200,10 +1254,16 @@ VKT_FN uint32_t estimate_texel(const Bc7KernelParams &P, const Texel t, uint32_t
 }
 
 // UNI: `part` is warp-uniform (lists from __constant__ memory, uniform loop control); otherwise lane-varying (shared memory).
-template<bool M7, bool PERC, bool KEY28, bool UNI, int STRIDE>
-VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part)
+template<bool M7, bool PERC, int KV, bool UNI, int STRIDE>
+VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part, uint64_t best_so_far)
 {
     constexpr int N = M7 ? 4 : 8;
+    constexpr bool KEY28 = (KV == kKvKey28);
+    // kKvExt keeps the reference's early-outs (a subset's running sum above the best error so far ends that subset,
+    // bc7enc.cpp:1536-1537 / :1573-1574 / :1673-1674 / :1705-1706; the second subset is skipped unless the first stayed
+    // below it, :1810): a low-frequency weight below 1 can make such a truncated sum the new minimum.  The other variants
+    // complete every sum -- with a weight of exactly 1 the argmin is the same.
+    constexpr bool EARLY = (KV == kKvExt);
     // UNI: texel pairs from __constant__ memory (one 64-bit broadcast load per trip, no index arithmetic)
     const EstPair *trips = VKT_UTAB(trips).t[UNI ? part : 0];
     const uint32_t tn = VKT_UTAB(trips).n[UNI ? part : 0];
@@ -1213,6 +1273,7 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
 #pragma unroll 1
     for(int s = 0; s < 2; ++s)
     {
+        if(EARLY && s && !(total < best_so_far)) { break; }
         const int k0 = s ? n0 : 0, k1 = s ? 16 : n0;                                           // !UNI: texel positions
         const uint32_t q0 = s ? (tn & 255u) : 0u, q1 = s ? (tn >> 8) : (tn & 255u);// UNI: pair positions
         // pass 1: bounding box, 16x2 SIMD lanes (r | g << 16) and (b | a << 16); an odd tail repeats its last texel
@@ -1295,12 +1356,16 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
         }
         else
         {
+            uint64_t sub = 0;
 #pragma unroll 1
             for(int k = k0; k < k1; ++k)
             {
                 const uint32_t e = estimate_texel<M7, PERC, N>(P, L.at(order[k]), axb, pal, thr);
-                total += (uint64_t) (int64_t) (int32_t) e;// `int ie; total_err += ie`, bc7enc.cpp:1533-1535
+                // perceptual: `int ie; total_err += ie` (bc7enc.cpp:1533-1535, sign-extended); linear: a uint32_t sum (:1572)
+                sub += PERC ? (uint64_t) (int64_t) (int32_t) e : (uint64_t) e;
+                if(EARLY && (sub > best_so_far)) { break; }
             }
+            total += sub;
         }
     }
     return total;
@@ -1316,12 +1381,15 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
 //                      block are spread over the lanes (lane-varying partition, the block's column read by all lanes as
 //                      a shared-memory broadcast) and the winner is a (error, iteration) warp minimum -- the same
 //                      "first strictly smaller wins" the sequential scan implements.
-template<bool M7, bool PERC, bool KEY28, int STRIDE>
+template<bool M7, bool PERC, int KV, int STRIDE>
 VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, bool active)
 {
     const uint32_t total_partitions = umin(P.max_partitions, 64u);
     if(total_partitions <= 1) { return 0; }
-    constexpr uint32_t kUniformIters = 35, kKeyIters = 14;
+    constexpr bool KEY28 = (KV == kKvKey28);
+    // (kKvExt: a candidate's early-outs depend on the best error of all candidates before it, so the whole scan stays in
+    // sequence per block)
+    constexpr uint32_t kUniformIters = (KV == kKvExt) ? 64 : 35, kKeyIters = 14;
     const uint32_t uniform_end = umin(total_partitions, kUniformIters);
     uint64_t best_err = kNoErr;
     uint32_t best_partition = 0, best_it = 0;
@@ -1394,8 +1462,9 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
             if(!warp_any(running) && !(regroup && it < kKeyIters)) { break; }// (a warp must not leave before the regrouping)
             continue;
         }
-        const uint64_t err = estimate_pair<M7, PERC, KEY28, true, STRIDE>(T, P, Lc, part);
-        // bc7enc.cpp:1817-1820 with m_low_frequency_partition_weight == 1.0f (the only value the C ABI accepts) is the identity
+        uint64_t err = estimate_pair<M7, PERC, KV, true, STRIDE>(T, P, Lc, part, best_err);
+        // bc7enc.cpp:1817-1820; with m_low_frequency_partition_weight == 1.0f (every variant but kKvExt) it is the identity
+        if((KV == kKvExt) && (part < 16)) { err = weigh_d(err, P.low_freq_weight); }
         if(need)
         {
             if(err < best_err) { best_err = err, best_partition = part, best_it = it; }
@@ -1436,7 +1505,7 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
                 const uint32_t it = base + lane;
                 if(it < total_partitions)
                 {
-                    const uint64_t err = estimate_pair<M7, PERC, KEY28, false, STRIDE>(T, P, Ls, VKT_UTAB(order)[it]);
+                    const uint64_t err = estimate_pair<M7, PERC, KV, false, STRIDE>(T, P, Ls, VKT_UTAB(order)[it], kNoErr);
                     const uint64_t k = (err << 6) | (uint64_t) it;// err < 2^36: no overflow
                     best_key = k < best_key ? k : best_key;
                 }
@@ -1568,7 +1637,7 @@ VKT_FN void pack_block(const Bc7Tables &T, const BlockSolution &s, uint32_t out[
 // mode 1 (bc7enc.cpp:2336-2397) / mode 7 (bc7enc.cpp:2193-2259): estimate, fit both subsets, arbitrate.
 // Called by the whole converged warp; lanes with want == false only help the estimator.
 // Returns the weighted error, or kNoErr when not better than best_err.
-template<int MODE, bool PERC, bool KEY28, bool UBER, int STRIDE>
+template<int MODE, bool PERC, int KV, bool UBER, int STRIDE>
 VKT_FN uint64_t two_subset_cells(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part, bool want, uint64_t best_err,
                                  BlockSolution &sol)
 {
@@ -1592,7 +1661,7 @@ VKT_FN uint64_t two_subset_cells(const Bc7Tables &T, const Bc7KernelParams &P, L
         const int s = pass ? second : 1 - second;
         const CellRef cell = {s ? perm1 : perm0, s ? n1 : n0};
         Cell r;
-        trial += compress_cell<MODE, ALPHA, PERC, KEY28, UBER, STRIDE>(T, P, L, cell, r);
+        trial += compress_cell<MODE, ALPHA, PERC, KV, UBER, STRIDE>(T, P, L, cell, r);
         if(s) { c[1] = r; }
         else { c[0] = r; }
         if(weigh(trial, mw) > best_err) { return kNoErr; }// bc7enc.cpp:2377/2234: cannot be adopted any more
@@ -1721,7 +1790,7 @@ VKT_FN bool block_has_alpha(const Bc7KernelParams &P, const uint32_t px[16])
 // ALPHA == true is handle_alpha_block (:2139-2291).  The caller classifies blocks first so that a warp only ever holds
 // blocks of one kind; the whole warp must call this converged (estimate_partition is warp-cooperative).
 // L: the lane column with texels [0,16) filled; the YCbCr part is filled here.
-template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int STRIDE>
+template<bool PERC, int KV, bool ALPHA, bool UBER, int STRIDE>
 VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
 {
     if(PERC) { prepare_lane<STRIDE>(L); }
@@ -1740,12 +1809,12 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     // the skipped estimates are worth more than the registers: measured).
     const bool do17 = ALPHA ? ((P.mode_mask & (1u << 7)) != 0) : ((P.max_partitions > 0) && (P.mode_mask & (1u << 1)));// warp-uniform
     uint32_t part17 = 0;
-    if(!ALPHA && do17) { part17 = estimate_partition<false, PERC, KEY28, STRIDE>(T, P, L, true); }
+    if(!ALPHA && do17) { part17 = estimate_partition<false, PERC, KV, STRIDE>(T, P, L, true); }
 
     if(P.mode_mask & (1u << 6))
     {
         Cell c6;
-        best_err = weigh(compress_cell<6, ALPHA, PERC, KEY28, UBER, STRIDE>(T, P, L, whole, c6), P.mode6_w);
+        best_err = weigh(compress_cell<6, ALPHA, PERC, KV, UBER, STRIDE>(T, P, L, whole, c6), P.mode6_w);
         sol.sel = c6.sel, sol.lo[0] = c6.lo, sol.hi[0] = c6.hi, sol.pbits[0] = c6.pbits;
     }
     if(!ALPHA)
@@ -1753,7 +1822,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         if(do17)
         {
             BlockSolution s1 = sol;
-            if(two_subset_cells<1, PERC, KEY28, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
+            if(two_subset_cells<1, PERC, KV, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s1) != kNoErr) { sol = s1; }
         }
     }
     else
@@ -1767,7 +1836,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
                 min_a = umin(min_a, a), max_a = umax(max_a, a);
             }
             Cell c5;
-            uint64_t e5 = compress_cell<5, false, PERC, KEY28, UBER, STRIDE>(T, P, L, whole, c5);
+            uint64_t e5 = compress_cell<5, false, PERC, KV, UBER, STRIDE>(T, P, L, whole, c5);
             uint32_t alo = 0, ahi = 0;
             uint64_t asel = 0;
             e5 += mode5_alpha<STRIDE>(T, P, L, min_a, max_a, alo, ahi, asel);
@@ -1784,9 +1853,9 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         }
         if(do17)
         {
-            part17 = estimate_partition<true, PERC, KEY28, STRIDE>(T, P, L, best_err > 0);
+            part17 = estimate_partition<true, PERC, KV, STRIDE>(T, P, L, best_err > 0);
             BlockSolution s7 = sol;
-            if(two_subset_cells<7, PERC, KEY28, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
+            if(two_subset_cells<7, PERC, KV, UBER, STRIDE>(T, P, L, part17, best_err > 0, best_err, s7) != kNoErr) { sol = s7; }
         }
     }
     pack_block(T, sol, out);

@@ -27,15 +27,33 @@ extern "C" void vkt_bc7_params_init(vkt_bc7_params *p) { vkt_bc7_params_init_inl
 namespace vkt
 {
 
-// Returns VKT_BCN_OK or VKT_BCN_ERR_UNSUPPORTED.  Weight setup follows bc7enc.cpp:2409-2420 (float constant expressions
+// Returns VKT_BCN_OK or VKT_BCN_ERR_INVALID.  Weight setup follows bc7enc.cpp:2409-2420 (float constant expressions
 // evaluated in float, truncating conversion) -- compile with -ffp-contract=off.
 inline int bc7_prepare_params(const vkt_bc7_params *p, Bc7KernelParams *k)
 {
-    // Knobs that only bc7enc_rdo's RDO post-processor drives and that vierkant never sets; they are rejected loudly
-    // instead of being silently ignored (see include/vierkant_bcn_cuda.h).
-    if(p->force_selectors || p->quant_mode6_endpoints) { return VKT_BCN_ERR_UNSUPPORTED; }
-    if(p->low_frequency_partition_weight != 1.0f) { return VKT_BCN_ERR_UNSUPPORTED; }
     if(p->uber_level > 4) { return VKT_BCN_ERR_INVALID; }
+    // The knobs bc7enc_rdo's RDO post-processor drives (vierkant never sets them): served by the extended kernel variant.
+    k->force_selectors = p->force_selectors != 0;
+    k->quant_mode6 = p->quant_mode6_endpoints != 0;
+    k->low_freq_weight = p->low_frequency_partition_weight;
+    k->forced_sel = 0;
+    k->m6_reduced = nullptr;// per device: set by the launcher
+    if(k->force_selectors)
+    {
+        // A forced selector indexes the palette of whichever mode is being tried (bc7enc.cpp:701-707); beyond that palette the
+        // reference reads an uninitialised colour.  Every selector must therefore exist in every mode the mask lets run.
+        uint32_t limit = 16;
+        if((p->mode_mask & (1u << 1)) && p->max_partitions > 0) { limit = 8; }
+        if(p->mode_mask & ((1u << 5) | (1u << 7))) { limit = 4; }
+        for(int i = 0; i < 16; ++i)
+        {
+            if(p->selectors[i] >= limit) { return VKT_BCN_ERR_INVALID; }
+            k->forced_sel |= (uint64_t) p->selectors[i] << (4 * i);
+        }
+    }
+    // (uint64_t)((double)err * weight + .5f), bc7enc.cpp:1819, is only defined for a finite, non-negative product in range
+    if(!(p->low_frequency_partition_weight >= 0.0f && p->low_frequency_partition_weight <= 65536.0f)) { return VKT_BCN_ERR_INVALID; }
+    k->ext = (k->force_selectors || k->quant_mode6 || p->low_frequency_partition_weight != 1.0f) ? 1u : 0u;
     const bool alpha_modes = (p->mode_mask & ((1u << 5) | (1u << 6) | (1u << 7))) != 0;
     const bool opaque_modes = (p->mode_mask & ((1u << 6) | (1u << 1))) != 0;
     if(!alpha_modes || !opaque_modes) { return VKT_BCN_ERR_INVALID; }// the reference asserts (bc7enc.cpp:2141,2295)

@@ -171,4 +171,26 @@ void bc7_tables_build(Bc7Tables *t)
     }
 }
 
+// g_mode6_reduced_quant, bc7enc.cpp:188-211: for every 11-bit endpoint position the nearest of 64 evenly spread 7-bit
+// levels, with the p-bit appended before the comparison; float arithmetic, first strict minimum wins.
+void bc7_m6_reduced_build(uint8_t *out)
+{
+    for(uint32_t p = 0; p < 2; ++p)
+    {
+        for(uint32_t i = 0; i < 2048; ++i)
+        {
+            const float target = static_cast<float>(i) / 2047.0f;
+            float best = 1e+9f;
+            int level = 0;
+            for(int j = 0; j < 64; ++j)
+            {
+                const int q = (j * 127 + 31) / 63;
+                const float d = std::fabs(static_cast<float>((q << 1) + static_cast<int>(p)) / 255.0f - target);
+                if(d < best) { best = d, level = q; }
+            }
+            out[i * 2 + p] = static_cast<uint8_t>(level);
+        }
+    }
+}
+
 }// namespace vkt

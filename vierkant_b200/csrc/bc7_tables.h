@@ -8,6 +8,7 @@
 // Reference: the tables bc7enc_compress_block_init() builds (/root/reference/extern/bc7enc_rdo/bc7enc.cpp:124-285) and
 // the static tables at bc7enc.cpp:48-105, 1714-1751, 1765-1775.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 namespace vkt
@@ -41,6 +42,10 @@ static_assert(sizeof(Bc7Tables) % 16 == 0, "copied to shared memory as uint4");
 
 // Filled on the host (product code, C++): vierkant_b200/csrc/bc7_tables.cpp
 void bc7_tables_build(Bc7Tables *t);
+// g_mode6_reduced_quant[2048][2] (bc7enc.cpp:188-211; only read with quant_mode6_endpoints): out[value * 2 + p], 4096 bytes.
+// Kept outside Bc7Tables: it is not copied to shared memory.
+constexpr size_t kBc7M6ReducedBytes = 2048 * 2;
+void bc7_m6_reduced_build(uint8_t *out);
 // The reference's float expression for the uber-level selector rescaling (bc7enc.cpp:1399), for checking the
 // integer-generated table in bc7_core.cuh: nibble s of the result is the rescaled selector.
 uint64_t bc7_uber_map_reference(int max_sel, int ly, int hy);

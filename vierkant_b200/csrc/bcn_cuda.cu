@@ -168,7 +168,7 @@ static_assert(offsetof(Bc7Tables, opt7) % 16 == 0, "table prefix is copied as ui
 
 // One lane == one block of the work list (list == nullptr: every block of the launch, in order).
 // UBER == false: the search without the uber-level stages (launched when uber_level == 0).
-template<bool PERC, bool KEY28, bool ALPHA, bool UBER, int NT>
+template<bool PERC, int KV, bool ALPHA, bool UBER, int NT>
 __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : (UBER ? kBc7CtasPerSmUber : kBc7CtasPerSm))
         bc7_encode_kernel(const __grid_constant__ Bc7Batch B, const Bc7KernelParams P, const Bc7Tables *__restrict__ g_tables,
                           const uint32_t *__restrict__ list, const uint32_t *__restrict__ count)
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : (UBER ? kBc7C
     load_block_texels<NT>(I.img, I.comps, I.stride, I.vec16 != 0, b % I.blocks_x, b / I.blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, KEY28, ALPHA, UBER, NT>(s_tables, P, lane, blk);
+    encode_block<PERC, KV, ALPHA, UBER, NT>(s_tables, P, lane, blk);
     if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
 }
 
@@ -205,10 +205,10 @@ constexpr size_t bc7_smem_bytes(bool alpha)
     return bc7_smem_table_bytes(alpha) + size_t(bc7_threads(alpha)) * 16 * sizeof(Texel) + (alpha ? sizeof(CtaScratch<kBc7ThreadsAlpha>) : sizeof(CtaScratch<kBc7Threads>));
 }
 
-template<bool PERC, bool KEY28, bool ALPHA, bool UBER>
+template<bool PERC, int KV, bool ALPHA, bool UBER>
 static cudaError_t bc7_kernel_attribute()
 {
-    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KEY28, ALPHA, UBER, bc7_threads(ALPHA)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(bc7_encode_kernel<PERC, KV, ALPHA, UBER, bc7_threads(ALPHA)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(bc7_smem_bytes(ALPHA)));
 }
 // > 48 KB of dynamic shared memory needs an explicit opt-in per kernel (and per device: called from context creation)
@@ -227,6 +227,10 @@ static cudaError_t bc7_kernel_attributes()
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true, true>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, false, true>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, false, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, kKvExt, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, kKvExt, true, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, kKvExt, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<false, kKvExt, true, true>(); }
 #endif
     return e;
 }
@@ -377,11 +381,12 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
     }
     Bc7KernelParams kp;
     const int rc = bc7_prepare_params(params, &kp);
-    if(rc == VKT_BCN_ERR_UNSUPPORTED)
+    if(rc)
     {
-        return fail(ctx, rc, "unsupported bc7 parameters (force_selectors / quant_mode6_endpoints / low_frequency_partition_weight != 1)");
+        return fail(ctx, rc, "invalid bc7 parameters (mode_mask must enable mode 6 or 1 and one of 5/6/7; uber_level <= 4; forced selectors "
+                             "must exist in every enabled mode's palette; 0 <= low_frequency_partition_weight <= 65536)");
     }
-    if(rc) { return fail(ctx, rc, "invalid bc7 parameters (mode_mask must enable mode 6 or 1 and one of 5/6/7; uber_level <= 4)"); }
+    kp.m6_reduced = reinterpret_cast<const uint8_t *>(s->d_tables + 1);
     for(uint32_t first = 0; first < num_images; first += kBc7MaxImages)
     {
         Bc7Batch B = {};
@@ -405,9 +410,17 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
             const uint32_t nt = uint32_t(bc7_threads(alpha)), grid = (B.total_blocks + nt - 1) / nt;
             auto go = [&](auto kernel) { kernel<<<grid, nt, bc7_smem_bytes(alpha), stream>>>(B, kp, s->d_tables, list, cnt); };
             // uber-free kernels exist for the 28-bit-key variants (every sane weight set); the wide-error ones always carry the stages
-            const int sel = ((kp.uber_level == 0 && kp.key28) ? 8 : 0) | (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            int sel = ((kp.uber_level == 0 && kp.key28) ? 8 : 0) | (params->perceptual ? 4 : 0) | (kp.key28 ? 2 : 0) | (alpha ? 1 : 0);
+            // forced selectors / reduced mode-6 quantisation / low-frequency partition weight: the extended variant (wide errors, uber stages)
+            if(kp.ext) { sel = 16 | (params->perceptual ? 2 : 0) | (alpha ? 1 : 0); }
             switch(sel)
             {
+#ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY
+                case 19: go(bc7_encode_kernel<true, kKvExt, true, true, kBc7ThreadsAlpha>); break;
+                case 18: go(bc7_encode_kernel<true, kKvExt, false, true, kBc7Threads>); break;
+                case 17: go(bc7_encode_kernel<false, kKvExt, true, true, kBc7ThreadsAlpha>); break;
+                case 16: go(bc7_encode_kernel<false, kKvExt, false, true, kBc7Threads>); break;
+#endif
                 case 15: go(bc7_encode_kernel<true, true, true, false, kBc7ThreadsAlpha>); break;
                 case 14: go(bc7_encode_kernel<true, true, false, false, kBc7Threads>); break;
 #ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY// (tuning builds compile the two default-parameter kernels only)
@@ -494,8 +507,15 @@ static cudaError_t init_slot(vkt::DeviceSlot *s, const vkt::Bc7Tables &host_tabl
     if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream4, cudaStreamNonBlocking); }
     if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream5, cudaStreamNonBlocking); }
     if(e == cudaSuccess) { e = cudaStreamCreateWithFlags(&s->stream6, cudaStreamNonBlocking); }
-    if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables)); }
+    // [Bc7Tables][reduced mode-6 quantiser table] in one allocation (the second one stays in global memory: kKvExt only)
+    if(e == cudaSuccess) { e = cudaMalloc(reinterpret_cast<void **>(&s->d_tables), sizeof(Bc7Tables) + kBc7M6ReducedBytes); }
     if(e == cudaSuccess) { e = cudaMemcpy(s->d_tables, &host_tables, sizeof(Bc7Tables), cudaMemcpyHostToDevice); }
+    if(e == cudaSuccess)
+    {
+        std::vector<uint8_t> m6(kBc7M6ReducedBytes);
+        bc7_m6_reduced_build(m6.data());
+        e = cudaMemcpy(s->d_tables + 1, m6.data(), kBc7M6ReducedBytes, cudaMemcpyHostToDevice);
+    }
     if(e == cudaSuccess) { e = bc7_kernel_attributes(); }
     if(e == cudaSuccess)
     {
