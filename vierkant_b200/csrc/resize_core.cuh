@@ -76,8 +76,14 @@ __global__ void __launch_bounds__(256) resize_h_kernel(const uint8_t *__restrict
         for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(resize_decode_u8(v[c]), w)); }
     }
     float *o = band + (size_t(r) * size_t(out_w) + size_t(x)) * C;
+    // (the band comes from cudaMalloc and a sample is C floats: 16-byte / 8-byte aligned for C == 4 / 2)
+    if(C == 4) { *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1 % C], acc[2 % C], acc[3 % C]); }
+    else if(C == 2) { *reinterpret_cast<float2 *>(o) = make_float2(acc[0], acc[1 % C]); }
+    else
+    {
 #pragma unroll
-    for(int c = 0; c < C; ++c) { o[c] = acc[c]; }
+        for(int c = 0; c < C; ++c) { o[c] = acc[c]; }
+    }
 }
 
 // Vertical pass + encode: output rows [y0, y0 + rows), one thread per (output row, column).
@@ -99,8 +105,26 @@ __global__ void __launch_bounds__(256) resize_v_kernel(const float *__restrict__
         const int2 tp = __ldg(tap + t);
         const float *p = band + (size_t(tp.x - band_row0) * size_t(out_w) + size_t(x)) * C;
         const float w = __int_as_float(tp.y);
+        // one 128-bit (64-bit) load per tap: a warp's 32 samples are then 4 (2) cache lines in one request instead of
+        // four strided 32-bit requests over the same lines
+        float v[C];
+        if(C == 4)
+        {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+            v[0] = q.x, v[1 % C] = q.y, v[2 % C] = q.z, v[3 % C] = q.w;
+        }
+        else if(C == 2)
+        {
+            const float2 q = __ldg(reinterpret_cast<const float2 *>(p));
+            v[0] = q.x, v[1 % C] = q.y;
+        }
+        else
+        {
 #pragma unroll
-        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(p[c], w)); }
+            for(int c = 0; c < C; ++c) { v[c] = p[c]; }
+        }
+#pragma unroll
+        for(int c = 0; c < C; ++c) { acc[c] = __fadd_rn(acc[c], __fmul_rn(v[c], w)); }
     }
     uint32_t q[C];
 #pragma unroll
