@@ -441,6 +441,18 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         uint8_t *lvl0 = d_lvl + lvl_off[0];
         const size_t row_px0 = size_t(w0) * comps * 4, row_blk0 = size_t(w0 / 4) * 16;
         uint32_t lane = 0;
+        // Level 1 (three quarters of the remaining levels' work) follows level 0 band by band on the same stream: once the
+        // graded bands have produced level-0 rows [bands[0].y0, y), every level-1 row whose taps stay inside that range is
+        // resized.  The level is then complete when level 0 is (one device) or right after the halo bands (several), and
+        // its encode starts about a millisecond earlier than behind the whole chain of ever smaller resize launches.
+        // l1_a .. l1_b: the rows of level 1 done this way (tap ranges ascend with the output row).
+        uint32_t l1_a = 0, l1_b = 0;
+        if(M > 1)
+        {
+            l1_a = need[1].first;
+            while(l1_a < need[1].second && uint32_t(ay[1]->first_in[l1_a]) < bands[0].y0) { ++l1_a; }
+            l1_b = l1_a;
+        }
         for(uint32_t k = 0; k < K && !rc; ++k)
         {
             if((rc = upload(k))) { break; }
@@ -448,10 +460,23 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, ready[k], 0));
             if((rc = resize_device(ctx, s, d_src, width, height, comps, lvl0, w0, h0, s->stream, bands[k].y0, bands[k].y1))) { break; }
             if(!bands[k].encode) { continue; }
-            const uint32_t e0 = bands[k].y0 / 4, e1 = bands[k].y1 / 4;
             cudaEvent_t resized;
             VKT_CUDA(ctx, new_event(&resized, "resize done", k));
             VKT_CUDA(ctx, cudaEventRecord(resized, s->stream));
+            if(M > 1)
+            {
+                uint32_t b = l1_b;
+                while(b < need[1].second && uint32_t(ay[1]->last_in[b]) < bands[k].y1) { ++b; }
+                if(b > l1_b)
+                {
+                    if((rc = resize_device(ctx, s, lvl0, w0, h0, comps, d_lvl + lvl_off[1], plan.level_width[1], plan.level_height[1], s->stream, l1_b, b)))
+                    {
+                        break;
+                    }
+                    l1_b = b;
+                }
+            }
+            const uint32_t e0 = bands[k].y0 / 4, e1 = bands[k].y1 / 4;
             cudaStream_t enc = (lane % 3u == 0) ? s->stream4 : ((lane % 3u == 1) ? s->stream5 : s->stream6);
             ++lane;
             VKT_CUDA(ctx, cudaStreamWaitEvent(enc, resized, 0));
@@ -481,15 +506,41 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         {
             const uint32_t w = plan.level_width[l], h = plan.level_height[l];
             uint8_t *cur = d_lvl + lvl_off[l];
-            if((rc = resize_device(ctx, s, d_lvl + lvl_off[l - 1], plan.level_width[l - 1], plan.level_height[l - 1], comps, cur, w, h, s->stream,
-                                   need[l].first, need[l].second)))
+            const uint8_t *prev = d_lvl + lvl_off[l - 1];
+            const uint32_t pw = plan.level_width[l - 1], ph = plan.level_height[l - 1];
+            if(l == 1 && l1_b > l1_a)
             {
-                break;
+                // what the band loop left: rows that read the halo bands
+                if(need[1].first < l1_a && (rc = resize_device(ctx, s, prev, pw, ph, comps, cur, w, h, s->stream, need[1].first, l1_a))) { break; }
+                if(l1_b < need[1].second && (rc = resize_device(ctx, s, prev, pw, ph, comps, cur, w, h, s->stream, l1_b, need[1].second))) { break; }
             }
+            else if((rc = resize_device(ctx, s, prev, pw, ph, comps, cur, w, h, s->stream, need[l].first, need[l].second))) { break; }
             const uint32_t r0 = own[l].first, r1 = own[l].second;
             const size_t row_px = size_t(w) * comps * 4, row_blk = size_t(w / 4) * 16;
+            const DevImage img{cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk};
+            if(l == 1 && M > 2 && uint64_t(r1 - r0) * (w / 4) >= (1u << 16))
+            {
+                // a large level 1 is encoded on its own, on an encode lane, while the chain of small levels is still being resized
+                cudaEvent_t l1_ready, l1_done;
+                VKT_CUDA(ctx, new_event(&l1_ready, "level 1 resized"));
+                VKT_CUDA(ctx, cudaEventRecord(l1_ready, s->stream));
+                cudaStream_t enc = (lane % 3u == 0) ? s->stream4 : ((lane % 3u == 1) ? s->stream5 : s->stream6);
+                ++lane;
+                VKT_CUDA(ctx, cudaStreamWaitEvent(enc, l1_ready, 0));
+                if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, &img, 1, params, enc); }
+                else { rc = launch_bc5(ctx, s, img.d_px, img.w, img.h, img.comps, img.stride, img.d_out, enc); }
+                if(rc) { break; }
+                VKT_CUDA(ctx, new_event(&l1_done, "level 1 encode done"));
+                VKT_CUDA(ctx, cudaEventRecord(l1_done, enc));
+                VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, l1_done, 0));
+                const size_t bytes = size_t(r1 - r0) * row_blk;
+                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[1]) + size_t(r0) * row_blk, img.d_out, bytes, cudaMemcpyDeviceToHost, s->stream3));
+                count(ctx, 0, 0, bytes);
+                mark(s->stream3, "level 1 download done");
+                continue;
+            }
             slices.push_back({l, r0, r1});
-            dev.push_back({cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk});
+            dev.push_back(img);
         }
         if(rc) { break; }
         mark(s->stream, "mip resizes done");
