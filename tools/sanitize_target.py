@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small run of every kernel for compute-sanitizer: BC7 (opaque + alpha, default and uber), BC5, the resize chain through
+"""Small run of every kernel for compute-sanitizer: BC7 (opaque + alpha, default, uber and extended variant), BC5, the resize chain through
 compress(), and compress_batch.  Usage: compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_target.py"""
 import os
 import sys
@@ -11,7 +11,15 @@ with capi.BcnContext([0]) as ctx:
     a, b = synth.make_texture(256, 128, 0), synth.make_texture(132, 68, 1)
     ctx.encode_bc7(a)
     ctx.encode_bc7(b, capi.default_params(uber_level=2, mode17_partition_estimation_filterbank=0))
+    # the extended kernel variant: forced selectors + reduced mode-6 quantisation + low-frequency partition weight, both metrics
+    ctx.encode_bc7(b, capi.default_params(force_selectors=1, selectors=[3, 3, 2, 2, 1, 1, 0, 0, 0, 1, 2, 3, 3, 2, 1, 0], quant_mode6_endpoints=1,
+                                          low_frequency_partition_weight=0.8, uber_level=1))
+    ctx.encode_bc7(b, capi.default_params(low_frequency_partition_weight=0.6, perceptual=0, weights=[1, 1, 1, 1]))
     ctx.encode_bc5(b)
+    # a chain large enough for the band pipeline (graded level-0 bands, level 1 resized band by band, its own encode lane)
+    # (VKT_SAN_BIG=1, memcheck only: 2048^2 reaches the separate level-1 encode lane)
+    n = 2048 if os.environ.get("VKT_SAN_BIG") else 512
+    ctx.compress(synth.make_texture(2 * n if n < 2048 else n, n, 1), capi.MODE_BC7, True)
     ctx.compress(b, capi.MODE_BC7, True)
     ctx.compress_batch([a, b, a[..., :3]], [capi.MODE_BC7, capi.MODE_BC5, capi.MODE_BC7], True)
 print("ok")
