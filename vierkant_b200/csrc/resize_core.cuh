@@ -17,6 +17,7 @@
 // :1737-1763).  Both passes are a few taps per sample and far below the encode kernels' cost; they are HBM-light because
 // only a band of rows is kept in fp32.
 #pragma once
+#include <chrono>
 #include <map>
 #include <memory>
 
@@ -319,12 +320,27 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     // graded split of the block rows [r0, r1): 1, 2, 3, 4 ... 4, 3, 2, 1 thirty-seconds when there is enough work
     auto graded = [&](uint32_t r0, uint32_t r1, std::vector<Band> &out) {
         static const uint8_t kBig[] = {1, 3, 6, 10, 14, 18, 22, 26, 29, 31, 32};// cumulative 32nds
+        static const uint8_t kQuarters[] = {8, 16, 24, 32};
         static const uint8_t kMid[] = {16, 32};
         static const uint8_t kOne[] = {32};
+        // measured (profiles/r1_ss_sweep.txt): a band needs enough CTAs to be worth its launches and its block latency --
+        // 4096^2 wants the graded schedule, 2048^2 four equal bands (1.09 -> 1.00 ms), 1024^2 two, 512^2 one (0.32 -> 0.28 ms)
         const uint64_t blocks = uint64_t(r1 - r0) * (plan.level_width[0] / 4);
-        const bool big = blocks >= (1u << 18), mid = blocks >= (1u << 14);
-        const uint8_t *f = big ? kBig : (mid ? kMid : kOne);
-        const size_t nf = big ? sizeof(kBig) : (mid ? sizeof(kMid) : sizeof(kOne));
+        const bool big = blocks >= (1u << 19), quarters = blocks >= (1u << 17), mid = blocks >= (1u << 15);
+        const uint8_t *f = big ? kBig : (quarters ? kQuarters : (mid ? kMid : kOne));
+        size_t nf = big ? sizeof(kBig) : (quarters ? sizeof(kQuarters) : (mid ? sizeof(kMid) : sizeof(kOne)));
+        // tuning experiments only: VKT_BCN_BANDS="2,8,16,24,30,32" (cumulative 32nds) replaces the schedule
+        uint8_t custom[32];
+        if(const char *e = getenv("VKT_BCN_BANDS"))
+        {
+            size_t n = 0;
+            for(const char *q = e; *q && n < sizeof(custom);)
+            {
+                custom[n++] = uint8_t(strtoul(q, const_cast<char **>(&q), 10));
+                if(*q == ',') { ++q; }
+            }
+            if(n && custom[n - 1] == 32) { f = custom, nf = n; }
+        }
         uint32_t prev = r0;
         for(size_t k = 0; k < nf; ++k)
         {
@@ -518,9 +534,14 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             const uint32_t r0 = own[l].first, r1 = own[l].second;
             const size_t row_px = size_t(w) * comps * 4, row_blk = size_t(w / 4) * 16;
             const DevImage img{cur + size_t(r0) * row_px, w, (r1 - r0) * 4, comps, w * comps, static_cast<uint8_t *>(s->d_out) + out_off[l] + size_t(r0) * row_blk};
-            if(l == 1 && M > 2 && uint64_t(r1 - r0) * (w / 4) >= (1u << 16))
+            // Level 1 of a 2048^2 .. 4096^2 texture is encoded on its own, on an encode lane, while the chain of small levels is
+            // still being resized (measured, profiles/r1_tt_sweep.txt: +3 % at both sizes).  A larger one stays with the other
+            // levels on the prioritised stream: queued behind every level-0 band it would end the call with a long download
+            // (8192^2: -2 %; a prioritised lane of its own measured no better, profiles/r1_uu_sweep.txt).
+            static const uint64_t l1_lane_min = getenv("VKT_BCN_L1_LANE_MIN") ? strtoull(getenv("VKT_BCN_L1_LANE_MIN"), nullptr, 10) : (1u << 16);// (tuning)
+            const uint64_t l1_blocks = uint64_t(r1 - r0) * (w / 4);
+            if(l == 1 && M > 2 && l1_blocks >= l1_lane_min && l1_blocks < (1u << 19))
             {
-                // a large level 1 is encoded on its own, on an encode lane, while the chain of small levels is still being resized
                 cudaEvent_t l1_ready, l1_done;
                 VKT_CUDA(ctx, new_event(&l1_ready, "level 1 resized"));
                 VKT_CUDA(ctx, cudaEventRecord(l1_ready, s->stream));
@@ -650,11 +671,16 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
     std::vector<std::unique_lock<std::mutex>> locks;
     for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
     std::vector<std::pair<cudaEvent_t, std::string>> marks;
+    const auto h0 = std::chrono::steady_clock::now();
     int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, &marks);
+    const auto h1 = std::chrono::steady_clock::now();
     const int rw = chain_wait(ctx, ctx->slots);
     if(!rc) { rc = rw; }
     if(!marks.empty() && ctx->slots.size() == 1)// VKT_BCN_TRACE=1
     {
+        const auto h2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vkt trace] host: everything queued after %.3f ms, waited until %.3f ms\n", std::chrono::duration<double, std::milli>(h1 - h0).count(),
+                std::chrono::duration<double, std::milli>(h2 - h0).count());
         for(const auto &m: marks)
         {
             float ms = 0.0f;
