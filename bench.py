@@ -19,6 +19,7 @@ data path; weak scaling) and `value` is the whole-job pixel rate over the max-ov
   roofline     : ALU/issue-slot bound: algorithmic lane-ops per launch / kernel time vs a peak
                  microbenchmarked in this run; HBM GB/s alongside (informational).
   cpu_baseline : the reference (oracle/_ref, unmodified sources) or the C port, on a bounded sample, on rank 0 at N=1.
+  parity       : the reference's output of that sample compared block by block with the same call on the GPU (untimed).
 """
 from __future__ import annotations
 
@@ -179,9 +180,10 @@ def cpu_baseline_sample(threads: int | None = None, reps: int = 2):
         best = None
         for _ in range(reps):
             t0 = time.perf_counter()
-            ref.compress(crop, 1, True, cores)
+            result = ref.compress(crop, 1, True, cores)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
+        levels = result["levels"]
         kind = "reference"
         what = ("vierkant::bcn::compress (unmodified reference, oracle/_ref) of a 2048x2048 crop + 10 mip levels "
                 f"(5.59 Mpixel), ThreadPoolClassic delegate with {cores} threads, stbir included, best of {reps}")
@@ -198,8 +200,9 @@ def cpu_baseline_sample(threads: int | None = None, reps: int = 2):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         kind = "port"
+        levels = None
         what = f"C port of bc7enc_compress_block over the 262144 blocks of a 2048x2048 crop, {cores} threads, best of {reps}"
-    return npix / best * 1e-6, {"cores": cores, "kind": kind, "sample": what, "seconds": best}
+    return npix / best * 1e-6, {"cores": cores, "kind": kind, "sample": what, "seconds": best}, crop, levels
 
 
 def run_reference(args):
@@ -453,8 +456,18 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
             try:
-                v, info = cpu_baseline_sample()
+                v, info, crop, ref_levels = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", **info}
+                if ref_levels is not None:
+                    # the reference's output of the baseline sample doubles as an in-run parity check (untimed): the same crop
+                    # through the same C-ABI call the e2e figure times, compared block by block
+                    _, ours = ctx.compress(crop, capi.MODE_BC7, True, params)
+                    total = sum(int(a.shape[0]) for a in ref_levels)
+                    bad = sum(int((np.asarray(a).reshape(-1, 16) != np.asarray(b).reshape(-1, 16)).any(axis=1).sum())
+                              for a, b in zip(ours, ref_levels))
+                    line["parity"] = {"against": "unmodified reference (oracle/_ref), vierkant::bcn::compress of the cpu_baseline sample",
+                                      "levels": len(ref_levels), "blocks": total, "mismatched_blocks": bad,
+                                      "bit_exact": bool(bad == 0 and len(ours) == len(ref_levels))}
             except Exception as e:  # the baseline must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line))
