@@ -540,7 +540,8 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             // (8192^2: -2 %; a prioritised lane of its own measured no better, profiles/r1_uu_sweep.txt).
             static const uint64_t l1_lane_min = getenv("VKT_BCN_L1_LANE_MIN") ? strtoull(getenv("VKT_BCN_L1_LANE_MIN"), nullptr, 10) : (1u << 16);// (tuning)
             const uint64_t l1_blocks = uint64_t(r1 - r0) * (w / 4);
-            if(l == 1 && M > 2 && l1_blocks >= l1_lane_min && l1_blocks < (1u << 19))
+            static const uint64_t l1_lane_max = getenv("VKT_BCN_L1_LANE_MAX") ? strtoull(getenv("VKT_BCN_L1_LANE_MAX"), nullptr, 10) : (1u << 19);// (tuning)
+            if(l == 1 && M > 2 && l1_blocks >= l1_lane_min && l1_blocks < l1_lane_max)
             {
                 cudaEvent_t l1_ready, l1_done;
                 VKT_CUDA(ctx, new_event(&l1_ready, "level 1 resized"));
