@@ -137,7 +137,12 @@ int vkt_bcn_cuda_resize_u8(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t wid
 /* The whole of vierkant::bcn::compress() (texture_block_compression.cpp:64-154): round the size up to a multiple of 4,
  * resize level 0 and every further level from the previous one (on the GPU, stbir-exact), encode every level.
  * Call vkt_bcn_cuda_compress_plan first to get the level count and per-level block counts, then pass
- * level_blocks[l] buffers of 16 * num_blocks[l] bytes.  Only the source image crosses PCIe on the way in. */
+ * level_blocks[l] buffers of 16 * num_blocks[l] bytes.  Only the source image crosses PCIe on the way in.
+ * `pixels` and every `level_blocks[l]` may be host memory (pinned for full speed, pageable works) or CUDA device memory
+ * (unified addressing decides per pointer): with device destinations -- for instance the VkBuffer vierkant uploads from,
+ * exported with VK_KHR_external_memory_fd and mapped by cudaImportExternalMemory / cudaExternalMemoryGetMappedBuffer --
+ * the blocks never touch the host (what create_compressed_texture's staging copy costs today,
+ * src/model/model_loading.cpp:483-488).  Same for vkt_bcn_cuda_compress_batch. */
 typedef struct vkt_bcn_plan
 {
     uint32_t base_width, base_height, num_levels;

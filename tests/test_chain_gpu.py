@@ -132,3 +132,27 @@ def test_compress_batch_matches_per_texture_calls(ctx, port_oracle):
     single = ctx.compress_batch(imgs[:3], capi.MODE_BC7, False)
     assert [len(l) for l in single] == [1, 1, 1] and np.array_equal(single[0][0], got[0][0])
     assert ctx.compress_batch([], capi.MODE_BC7, True) == []
+
+
+@pytest.mark.parametrize("w,h,c,mips", [(1024, 512, 4, True), (124, 84, 3, True), (2048, 2048, 4, True), (64, 64, 4, False)])
+def test_compress_accepts_device_source_and_device_destinations(ctx, w, h, c, mips):
+    """SURVEY.md 8f N4, the CUDA half: `pixels` and `level_blocks[l]` may be device memory (e.g. an imported Vulkan buffer);
+    the blocks are the ones the host-to-host call returns."""
+    import ctypes as C
+
+    import torch
+    img = synth.make_texture(w, h, 1, seed=w + h)[..., :c]
+    plan, want = ctx.compress(img, capi.MODE_BC7, mips)
+    d_img = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+    d_out = [torch.zeros((int(plan.level_num_blocks[l]), 16), dtype=torch.uint8, device="cuda") for l in range(plan.num_levels)]
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * plan.num_levels)(*[t.data_ptr() for t in d_out])
+    ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, d_img.data_ptr(), w, h, c, int(mips), None, ptrs))
+    for l in range(plan.num_levels):
+        assert np.array_equal(d_out[l].cpu().numpy(), want[l]), l
+    # mixed: device source, host destinations
+    h_out = [np.zeros((int(plan.level_num_blocks[l]), 16), dtype=np.uint8) for l in range(plan.num_levels)]
+    ptrs = (C.c_void_p * plan.num_levels)(*[a.ctypes.data for a in h_out])
+    ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, d_img.data_ptr(), w, h, c, int(mips), None, ptrs))
+    for l in range(plan.num_levels):
+        assert np.array_equal(h_out[l], want[l]), l

@@ -275,6 +275,10 @@ static int resize_host(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t w, uint
 // device-to-device traffic is needed ("halo recompute" taken to the whole chain).
 // Queue one chain on `slots` (one slot per participating device; the caller holds their mutexes).  Nothing is waited for:
 // chain_wait() does that.
+// `pixels` and `level_blocks[l]` may be host memory (pinned for full speed) or device memory of any device of the context:
+// the copies that read / write them are issued with cudaMemcpyDefault (unified addressing), so a caller that owns a device
+// buffer -- e.g. a Vulkan staging or image buffer imported with cudaImportExternalMemory -- gets its
+// blocks without a trip through the host.
 static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots, uint32_t mode, const uint8_t *pixels, uint32_t width,
                          uint32_t height, uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks,
                          std::vector<std::pair<cudaEvent_t, std::string>> *marks_out)
@@ -445,7 +449,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             for(const auto &t: todo)
             {
                 VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(t.first) * src_row, pixels + size_t(t.first) * src_row,
-                                              size_t(t.second - t.first) * src_row, cudaMemcpyHostToDevice, s->stream2));
+                                              size_t(t.second - t.first) * src_row, cudaMemcpyDefault, s->stream2));
                 count(ctx, 0, size_t(t.second - t.first) * src_row, 0);
                 have.push_back(t);
             }
@@ -506,7 +510,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             VKT_CUDA(ctx, cudaEventRecord(enc_done, enc));
             VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, enc_done, 0));
             VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[0]) + size_t(e0) * row_blk0, d_blk, size_t(e1 - e0) * row_blk0,
-                                          cudaMemcpyDeviceToHost, s->stream3));
+                                          cudaMemcpyDefault, s->stream3));
             count(ctx, 0, 0, size_t(e1 - e0) * row_blk0);
             mark(s->stream3, "download done", k);
         }
@@ -556,7 +560,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
                 VKT_CUDA(ctx, cudaEventRecord(l1_done, enc));
                 VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, l1_done, 0));
                 const size_t bytes = size_t(r1 - r0) * row_blk;
-                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[1]) + size_t(r0) * row_blk, img.d_out, bytes, cudaMemcpyDeviceToHost, s->stream3));
+                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[1]) + size_t(r0) * row_blk, img.d_out, bytes, cudaMemcpyDefault, s->stream3));
                 count(ctx, 0, 0, bytes);
                 mark(s->stream3, "level 1 download done");
                 continue;
@@ -598,7 +602,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
                 const Slice &sl = slices[k];
                 const size_t row_blk = size_t(plan.level_width[sl.level] / 4) * 16, bytes = size_t(sl.r1 - sl.r0) * row_blk;
                 VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[sl.level]) + size_t(sl.r0) * row_blk, dev[k].d_out, bytes,
-                                              cudaMemcpyDeviceToHost, s->stream));
+                                              cudaMemcpyDefault, s->stream));
                 count(ctx, 0, 0, bytes);
             }
             mark(s->stream, "mip download done");
@@ -640,7 +644,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         for(uint32_t l = M; l < L && !rc; ++l)
         {
             const size_t bytes = size_t(plan.level_num_blocks[l]) * 16;
-            VKT_CUDA(ctx, cudaMemcpyAsync(level_blocks[l], static_cast<uint8_t *>(s->d_out) + out_off[l], bytes, cudaMemcpyDeviceToHost, s->stream));
+            VKT_CUDA(ctx, cudaMemcpyAsync(level_blocks[l], static_cast<uint8_t *>(s->d_out) + out_off[l], bytes, cudaMemcpyDefault, s->stream));
             count(ctx, 0, 0, bytes);
         }
     }
