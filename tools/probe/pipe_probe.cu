@@ -24,6 +24,9 @@ __device__ __forceinline__ void step(uint32_t &a, uint32_t &b, uint32_t k)
     if(OP == 11) { a = __mulhi((int) a, 1 << 24) + b; }                       // IMAD.HI
     if(OP == 12) { int d = (int) (a - k) >> 8; b += (uint32_t) (d * d) * 103u; a += b; }// metric term: sub, shf, imad, imad, (add)
     if(OP == 13) { a = a * b + k; b = (uint32_t) ((int) b >> 3) + a; }        // IMAD + SHF + IADD
+    if(OP == 15) { asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(a) : "r"(k), "r"(b)); }                     // IDP.2A.LO.S16.U8
+    if(OP == 16) { asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(a) : "r"(k), "r"(b)); b = b ^ a; }         // IDP.2A + LOP3
+    if(OP == 17) { a = __dp4a(a, b, k); b = b ^ a; }                                                          // IDP.4A + LOP3
     if(OP == 14) { float f = __uint_as_float(a); f = __fmaf_rn(f, 1.0001f, 0.5f); a = __float_as_uint(f); }// FFMA
 }
 template<int OP>
@@ -148,6 +151,9 @@ int main()
         run<12>("metric term (sub shf imad imad add)", 5, c, p.multiProcessorCount, mhz, d);
         run<13>("IMAD + LEA", 2, c, p.multiProcessorCount, mhz, d);
         run<14>("FFMA", 1, c, p.multiProcessorCount, mhz, d);
+        run<15>("IDP.2A", 1, c, p.multiProcessorCount, mhz, d);
+        run<16>("IDP.2A + LOP3", 2, c, p.multiProcessorCount, mhz, d);
+        run<17>("IDP.4A + LOP3", 2, c, p.multiProcessorCount, mhz, d);
     }
     return 0;
 }
