@@ -92,12 +92,23 @@ def test_compress_known_answers(ctx, known):
 
 
 def test_compress_big_odd_size_is_banded_and_exact(ctx, port_oracle):
-    """>= 2^18 blocks: level 0 goes through the graded row bands (upload / resize / encode / download pipelined), here with
-    the Catmull-Rom upsample of an odd size (2050 x 2046 -> 2052 x 2048) in front."""
+    """2^17 .. 2^19 blocks: level 0 goes through four row bands (upload / resize / encode / download pipelined), level 1 is
+    resized band by band behind it and encoded on its own lane; here with the Catmull-Rom upsample of an odd size
+    (2050 x 2046 -> 2052 x 2048) in front."""
     img = synth.make_texture(2050, 2046, 1, seed=77)
     want = port_oracle.compress(img, 1, True, threads=os.cpu_count() or 1)
     plan, levels = ctx.compress(img, capi.MODE_BC7, True)
     assert (plan.base_width, plan.base_height, plan.num_levels) == (2052, 2048, len(want["levels"]))
+    for got, ref in zip(levels, want["levels"]):
+        assert np.array_equal(got, ref)
+
+
+def test_compress_graded_bands_are_exact(ctx, port_oracle):
+    """>= 2^19 blocks (4096 x 2048): the graded 11-band schedule of the large textures, level 1 following band by band."""
+    img = synth.make_texture(4096, 2048, 1, seed=78)
+    want = port_oracle.compress(img, 1, True, threads=os.cpu_count() or 1)
+    plan, levels = ctx.compress(img, capi.MODE_BC7, True)
+    assert plan.num_levels == len(want["levels"])
     for got, ref in zip(levels, want["levels"]):
         assert np.array_equal(got, ref)
 
