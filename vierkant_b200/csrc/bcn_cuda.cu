@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -24,6 +25,7 @@
 #include "bc5_core.cuh"
 #include "bc7_core.cuh"
 #include "bc7_params.h"
+#include "host_copy.h"
 
 namespace vkt
 {
@@ -281,6 +283,18 @@ struct DeviceSlot
     size_t in_cap = 0, out_cap = 0, tmp_cap = 0;
     std::vector<cudaEvent_t> event_pool;// ordering events of the pipelined chain (guarded by mtx like the buffers)
     size_t events_used = 0;
+    // pageable caller memory (host_copy.h): pinned staging for the source rows this device reads and for its blocks, and the
+    // copies from the block staging into the caller's buffers that chain_wait() still owes (each once its event has fired)
+    void *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0;
+    struct PendingCopy
+    {
+        cudaEvent_t ready;
+        const void *src;
+        void *dst;
+        size_t bytes;
+    };
+    std::vector<PendingCopy> pending;
     std::mutex mtx;
 };
 
@@ -296,6 +310,8 @@ struct vkt_bcn_ctx
     vkt_bcn_stats stats{};
     std::mutex stats_mtx;
     void *h_stage = nullptr;// pinned gather buffer of the multi-device chain (used with every slot mutex held)
+    std::unique_ptr<vkt::CopyPool> copy_pool;// made on first use (a caller with pageable buffers)
+    std::mutex copy_pool_mtx;
     size_t stage_cap = 0;
 };
 
@@ -339,6 +355,41 @@ static int ensure(vkt_bcn_ctx *ctx, void **ptr, size_t *cap, size_t need)
     VKT_CUDA(ctx, cudaMalloc(ptr, need));
     *cap = need;
     return VKT_BCN_OK;
+}
+
+static int ensure_pinned(vkt_bcn_ctx *ctx, void **ptr, size_t *cap, size_t need)
+{
+    if(*cap >= need) { return VKT_BCN_OK; }
+    if(*ptr) { VKT_CUDA(ctx, cudaFreeHost(*ptr)); }
+    *ptr = nullptr, *cap = 0;
+    VKT_CUDA(ctx, cudaHostAlloc(ptr, need, cudaHostAllocPortable));
+    *cap = need;
+    return VKT_BCN_OK;
+}
+
+// Host memory CUDA does not know (malloc, std::vector): copies from / to it would be staged by the driver on the calling thread.
+static bool is_pageable_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static CopyPool &copy_pool(vkt_bcn_ctx *ctx)
+{
+    std::lock_guard<std::mutex> g(ctx->copy_pool_mtx);
+    if(!ctx->copy_pool)
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned workers = std::min(7u, std::max(1u, hw / 2));
+        if(const char *e = getenv("VKT_BCN_COPY_THREADS")) { workers = unsigned(std::max(1, atoi(e))) - 1u; }// (tuning; 1 = caller only)
+        ctx->copy_pool = std::make_unique<CopyPool>(workers);
+    }
+    return *ctx->copy_pool;
 }
 
 static void count(vkt_bcn_ctx *ctx, uint64_t launches, uint64_t h2d, uint64_t d2h)
@@ -637,6 +688,8 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
             cudaFree(s->d_in);
             cudaFree(s->d_out);
             cudaFree(s->d_tmp);
+            if(s->h_in) { cudaFreeHost(s->h_in); }
+            if(s->h_out) { cudaFreeHost(s->h_out); }
             delete s->axis_cache;// frees the cached resize tables
         }
         delete s;

@@ -302,6 +302,11 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     }
     const uint32_t G = uint32_t(slots.size());
     const size_t src_bytes = size_t(width) * height * comps;
+    // Pageable caller memory (what the C++ drop-in passes: a malloc'ed image in, std::vector blocks out) is staged through
+    // pinned buffers of the slot with the copy pool (host_copy.h); pinned and device memory is used in place.
+    const bool stage_in = is_pageable_host(pixels);
+    bool stage_out[16] = {}, any_stage_out = false;
+    for(uint32_t l = 0; l < plan.num_levels; ++l) { stage_out[l] = is_pageable_host(level_blocks[l]), any_stage_out = any_stage_out || stage_out[l]; }
     size_t lvl_off[16], lvl_total = 0, out_off[16], out_total = 0;
     for(uint32_t l = 0; l < plan.num_levels; ++l)
     {
@@ -392,6 +397,22 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             ctx->stage_cap = need;
         }
     }
+    // blocks at d_ptr (inside slot sl's d_out) -> bytes [off, off + bytes) of the caller's level l, queued on st
+    auto fetch = [&](DeviceSlot *sl, uint32_t l, size_t off, const void *d_ptr, size_t bytes, cudaStream_t st) -> int {
+        uint8_t *user = static_cast<uint8_t *>(level_blocks[l]) + off;
+        if(stage_out[l])
+        {
+            uint8_t *staged = static_cast<uint8_t *>(sl->h_out) + (static_cast<const uint8_t *>(d_ptr) - static_cast<const uint8_t *>(sl->d_out));
+            VKT_CUDA(ctx, cudaMemcpyAsync(staged, d_ptr, bytes, cudaMemcpyDeviceToHost, st));
+            cudaEvent_t landed;
+            VKT_CUDA(ctx, new_event(&landed));
+            VKT_CUDA(ctx, cudaEventRecord(landed, st));
+            sl->pending.push_back({landed, staged, user, bytes});// chain_wait() moves it on once the event has fired
+        }
+        else { VKT_CUDA(ctx, cudaMemcpyAsync(user, d_ptr, bytes, cudaMemcpyDefault, st)); }
+        count(ctx, 0, 0, bytes);
+        return VKT_BCN_OK;
+    };
     for(uint32_t g = 0; g < Geff && !rc; ++g)
     {
         DeviceSlot *s = slots[g];
@@ -400,6 +421,8 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_total))) { break; }
         uint8_t *d_src = static_cast<uint8_t *>(s->d_in), *d_lvl = d_src + align_up(src_bytes, 256);
+        s->pending.clear();
+        if(any_stage_out && (rc = ensure_pinned(ctx, &s->h_out, &s->h_out_cap, out_total))) { break; }
         // vertical tap ranges of every sliced level: ay[l] maps rows of level l-1 (l == 0: the source) to rows of level l
         std::vector<const DeviceAxis *> ay(M, nullptr);
         for(uint32_t l = 0; l < M && !rc; ++l) { rc = get_axis(ctx, s, int(l ? plan.level_height[l - 1] : height), int(plan.level_height[l]), &ay[l]); }
@@ -422,6 +445,13 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         std::vector<std::pair<uint32_t, uint32_t>> have;// disjoint source-row intervals already queued for upload
         std::vector<cudaEvent_t> ready(K, nullptr);     // recorded on the upload stream once band k's source rows are queued
         std::vector<char> queued(K, 0);
+        uint32_t in_base = 0;// first source row held by the pinned input staging buffer
+        if(stage_in)
+        {
+            const std::pair<uint32_t, uint32_t> all = source_rows(taps[0], need[0].first, need[0].second, height);
+            in_base = all.first;
+            if((rc = ensure_pinned(ctx, &s->h_in, &s->h_in_cap, size_t(all.second - all.first) * src_row))) { break; }
+        }
         mark(s->stream2, "t0");
         auto upload = [&](uint32_t k) -> int {
             if(queued[k]) { return VKT_BCN_OK; }
@@ -448,7 +478,14 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             }
             for(const auto &t: todo)
             {
-                VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(t.first) * src_row, pixels + size_t(t.first) * src_row,
+                const uint8_t *from = pixels + size_t(t.first) * src_row;
+                if(stage_in)
+                {
+                    uint8_t *staged = static_cast<uint8_t *>(s->h_in) + size_t(t.first - in_base) * src_row;
+                    copy_pool(ctx).copy(staged, from, size_t(t.second - t.first) * src_row);
+                    from = staged;
+                }
+                VKT_CUDA(ctx, cudaMemcpyAsync(d_src + size_t(t.first) * src_row, from,
                                               size_t(t.second - t.first) * src_row, cudaMemcpyDefault, s->stream2));
                 count(ctx, 0, size_t(t.second - t.first) * src_row, 0);
                 have.push_back(t);
@@ -476,7 +513,9 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         for(uint32_t k = 0; k < K && !rc; ++k)
         {
             if((rc = upload(k))) { break; }
-            if(k + 1 < K && (rc = upload(k + 1))) { break; }// keep the link busy: queue the next upload before this band's kernels
+            // keep the link busy: queue the next upload before this band's kernels -- unless the source is pageable, where
+            // an upload starts with host work (the copy into the pinned staging buffer): that goes behind the launches
+            if(!stage_in && k + 1 < K && (rc = upload(k + 1))) { break; }
             VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, ready[k], 0));
             if((rc = resize_device(ctx, s, d_src, width, height, comps, lvl0, w0, h0, s->stream, bands[k].y0, bands[k].y1))) { break; }
             if(!bands[k].encode) { continue; }
@@ -509,10 +548,9 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             VKT_CUDA(ctx, new_event(&enc_done, "encode done", k));
             VKT_CUDA(ctx, cudaEventRecord(enc_done, enc));
             VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, enc_done, 0));
-            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[0]) + size_t(e0) * row_blk0, d_blk, size_t(e1 - e0) * row_blk0,
-                                          cudaMemcpyDefault, s->stream3));
-            count(ctx, 0, 0, size_t(e1 - e0) * row_blk0);
+            if((rc = fetch(s, 0, size_t(e0) * row_blk0, d_blk, size_t(e1 - e0) * row_blk0, s->stream3))) { break; }
             mark(s->stream3, "download done", k);
+            if(stage_in && k + 1 < K && (rc = upload(k + 1))) { break; }
         }
         if(rc) { break; }
         // sliced mip levels: resize the needed rows, then this device's block rows of every level in one set of launches
@@ -559,9 +597,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
                 VKT_CUDA(ctx, new_event(&l1_done, "level 1 encode done"));
                 VKT_CUDA(ctx, cudaEventRecord(l1_done, enc));
                 VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream3, l1_done, 0));
-                const size_t bytes = size_t(r1 - r0) * row_blk;
-                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[1]) + size_t(r0) * row_blk, img.d_out, bytes, cudaMemcpyDefault, s->stream3));
-                count(ctx, 0, 0, bytes);
+                if((rc = fetch(s, 1, size_t(r0) * row_blk, img.d_out, size_t(r1 - r0) * row_blk, s->stream3))) { break; }
                 mark(s->stream3, "level 1 download done");
                 continue;
             }
@@ -601,9 +637,8 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             {
                 const Slice &sl = slices[k];
                 const size_t row_blk = size_t(plan.level_width[sl.level] / 4) * 16, bytes = size_t(sl.r1 - sl.r0) * row_blk;
-                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(level_blocks[sl.level]) + size_t(sl.r0) * row_blk, dev[k].d_out, bytes,
-                                              cudaMemcpyDefault, s->stream));
-                count(ctx, 0, 0, bytes);
+                const int r = fetch(s, sl.level, size_t(sl.r0) * row_blk, dev[k].d_out, bytes, s->stream);
+                if(r) { return r; }
             }
             mark(s->stream, "mip download done");
             return VKT_BCN_OK;
@@ -644,8 +679,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         for(uint32_t l = M; l < L && !rc; ++l)
         {
             const size_t bytes = size_t(plan.level_num_blocks[l]) * 16;
-            VKT_CUDA(ctx, cudaMemcpyAsync(level_blocks[l], static_cast<uint8_t *>(s->d_out) + out_off[l], bytes, cudaMemcpyDefault, s->stream));
-            count(ctx, 0, 0, bytes);
+            rc = fetch(s, l, 0, static_cast<uint8_t *>(s->d_out) + out_off[l], bytes, s->stream);
         }
     }
     if(marks_out) { marks_out->swap(marks); }
@@ -658,7 +692,19 @@ static int chain_wait(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots)
     for(DeviceSlot *s: slots)
     {
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
-        cudaError_t e = cudaStreamSynchronize(s->stream);
+        // blocks staged for a pageable destination: hand each piece over as soon as it has landed, while the GPU still works
+        cudaError_t e = cudaSuccess;
+        for(const DeviceSlot::PendingCopy &pc: s->pending)
+        {
+            const cudaError_t e1 = cudaEventSynchronize(pc.ready);
+            if(e1 == cudaSuccess) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
+            else if(e == cudaSuccess) { e = e1; }
+        }
+        s->pending.clear();
+        {
+            const cudaError_t e0 = cudaStreamSynchronize(s->stream);
+            if(e == cudaSuccess) { e = e0; }
+        }
         for(cudaStream_t st: {s->stream2, s->stream3, s->stream4, s->stream5, s->stream6})
         {
             const cudaError_t e2 = cudaStreamSynchronize(st);
