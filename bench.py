@@ -20,6 +20,7 @@ data path; weak scaling) and `value` is the whole-job pixel rate over the max-ov
                  microbenchmarked in this run; HBM GB/s alongside (informational).
   cpu_baseline : the reference (oracle/_ref, unmodified sources) or the C port, on a bounded sample, on rank 0 at N=1.
   parity       : the reference's output of that sample compared block by block with the same call on the GPU (untimed).
+  e2e_pageable : the e2e call once more with pageable host buffers, as the C++ drop-in passes them (informational).
 """
 from __future__ import annotations
 
@@ -403,6 +404,20 @@ def main():
     b1 = ctx.stats()
     barrier()
 
+    # the same call with PAGEABLE host buffers -- what the C++ drop-in passes (a malloc'ed crocore image in, std::vector blocks out):
+    # informational, N = 1 / single-texture workloads only, outside every other timed region
+    pageable_ms = None
+    if world == 1 and batch_srcs is None and dims[0][0] <= 8192:
+        p_src = torch.from_numpy(host_levels[0][0].numpy().copy())  # plain (unpinned) host memory
+        p_outs = [torch.empty_like(o, pin_memory=False) for o in host_out]
+        p_ptrs = (C.c_void_p * len(p_outs))(*[o.data_ptr() for o in p_outs])
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                t0 = time.perf_counter()
+            ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, p_src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                     C.byref(params), p_ptrs))
+        pageable_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
     tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -438,6 +453,9 @@ def main():
                             "classify + encode on the GPU, pinned host blocks of all levels out") if NTEX == 1 else
                            ("vkt_bcn_cuda_compress_batch: the textures of the batch, each as in vierkant::bcn::compress() (pinned source in, "
                             "resize chain + encode on the GPU, pinned blocks out), pipelined over two lanes per device")},
+            "e2e_pageable": (None if pageable_ms is None else
+                             {"value": npix / (pageable_ms * 1e-3) * 1e-6, "unit": "Mpixel/s", "ms_per_step": pageable_ms,
+                              "note": "same call, pageable host buffers as the C++ drop-in passes them (staged by the library); informational"}),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",
