@@ -769,6 +769,8 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         }
     }
     int rc = VKT_BCN_OK;
+    std::vector<char> pageable_in(num_images), pageable_out(num_images);
+    for(uint32_t i = 0; i < num_images; ++i) { pageable_in[i] = is_pageable_host(images[i].pixels), pageable_out[i] = is_pageable_host(images[i].out_blocks); }
     std::vector<std::unique_lock<std::mutex>> locks;
     for(uint32_t g = 0; g < G; ++g) { locks.emplace_back(ctx->slots[g]->mtx); }
     for(uint32_t g = 0; g < G && !rc; ++g)
@@ -778,6 +780,12 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         VKT_CUDA(ctx, cudaSetDevice(s->device));
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, in_need[g]))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_need[g]))) { break; }
+        // pageable images / block buffers are staged through pinned mirrors of d_in / d_out (see host_copy.h)
+        bool page_in = false, page_out = false;
+        for(const Piece &p: plan[g]) { page_in = page_in || pageable_in[p.img], page_out = page_out || pageable_out[p.img]; }
+        if(page_in && (rc = ensure_pinned(ctx, &s->h_in, &s->h_in_cap, in_need[g]))) { break; }
+        if(page_out && (rc = ensure_pinned(ctx, &s->h_out, &s->h_out_cap, out_need[g]))) { break; }
+        s->pending.clear(), s->events_used = 0;
     }
     // queue group by group, round-robin over devices so that all PCIe links start early
     constexpr uint64_t kGroupBlocks = 1u << 20;
@@ -804,8 +812,21 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
                 const size_t row_bytes = size_t(img.width) * img.comps;
                 uint8_t *d_in = static_cast<uint8_t *>(s->d_in) + p.in_off;
                 // the device copy is tightly packed
-                VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, img.pixels + size_t(p.row0) * 4 * stride, stride, row_bytes, size_t(rows) * 4,
-                                                cudaMemcpyHostToDevice, st));
+                const uint8_t *from = img.pixels + size_t(p.row0) * 4 * stride;
+                if(pageable_in[p.img])
+                {
+                    uint8_t *staged = static_cast<uint8_t *>(s->h_in) + p.in_off;
+                    if(stride == row_bytes) { copy_pool(ctx).copy(staged, from, size_t(rows) * 4 * row_bytes); }
+                    else
+                    {
+                        for(size_t r = 0; r < size_t(rows) * 4; ++r) { memcpy(staged + r * row_bytes, from + r * stride, row_bytes); }
+                    }
+                    VKT_CUDA(ctx, cudaMemcpyAsync(d_in, staged, size_t(rows) * 4 * row_bytes, cudaMemcpyHostToDevice, st));
+                }
+                else
+                {
+                    VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, from, stride, row_bytes, size_t(rows) * 4, cudaMemcpyDefault, st));
+                }
                 dev.push_back({d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), static_cast<uint8_t *>(s->d_out) + p.out_off});
                 blocks += uint64_t(rows) * (img.width / 4);
                 count(ctx, 0, size_t(rows) * 4 * row_bytes, 0);
@@ -823,8 +844,22 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
                 const Piece &p = plan[g][k];
                 const vkt_bcn_image &img = images[p.img];
                 const size_t row_blk = size_t(img.width / 4) * 16, bytes = size_t(p.row1 - p.row0) * row_blk;
-                VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(img.out_blocks) + size_t(p.row0) * row_blk,
-                                              static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDeviceToHost, st));
+                uint8_t *user = static_cast<uint8_t *>(img.out_blocks) + size_t(p.row0) * row_blk;
+                if(pageable_out[p.img])
+                {
+                    uint8_t *staged = static_cast<uint8_t *>(s->h_out) + p.out_off;
+                    VKT_CUDA(ctx, cudaMemcpyAsync(staged, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDeviceToHost, st));
+                    if(s->events_used == s->event_pool.size())
+                    {
+                        cudaEvent_t fresh;
+                        VKT_CUDA(ctx, cudaEventCreateWithFlags(&fresh, cudaEventDisableTiming));
+                        s->event_pool.push_back(fresh);
+                    }
+                    cudaEvent_t landed = s->event_pool[s->events_used++];
+                    VKT_CUDA(ctx, cudaEventRecord(landed, st));
+                    s->pending.push_back({landed, staged, user, bytes});
+                }
+                else { VKT_CUDA(ctx, cudaMemcpyAsync(user, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDefault, st)); }
                 count(ctx, 0, 0, bytes);
             }
             more = more || next[g] < plan[g].size();
@@ -835,9 +870,16 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         DeviceSlot *s = ctx->slots[g];
         if(plan[g].empty()) { continue; }
         if(cudaSetDevice(s->device) != cudaSuccess) { continue; }
-        cudaError_t e = cudaStreamSynchronize(s->stream);
-        const cudaError_t e2 = cudaStreamSynchronize(s->stream2);
-        if(e == cudaSuccess) { e = e2; }
+        cudaError_t e = cudaSuccess;
+        for(const DeviceSlot::PendingCopy &pc: s->pending)// blocks staged for pageable destinations, each as soon as it has landed
+        {
+            const cudaError_t e1 = cudaEventSynchronize(pc.ready);
+            if(e1 == cudaSuccess) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
+            else if(e == cudaSuccess) { e = e1; }
+        }
+        s->pending.clear();
+        const cudaError_t e0 = cudaStreamSynchronize(s->stream), e2 = cudaStreamSynchronize(s->stream2);
+        if(e == cudaSuccess) { e = (e0 != cudaSuccess) ? e0 : e2; }
         if(e != cudaSuccess && !rc) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "stream synchronize failed: %s", cudaGetErrorString(e)); }
     }
     return rc;
