@@ -167,3 +167,23 @@ def test_compress_accepts_device_source_and_device_destinations(ctx, w, h, c, mi
     ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, d_img.data_ptr(), w, h, c, int(mips), None, ptrs))
     for l in range(plan.num_levels):
         assert np.array_equal(h_out[l], want[l]), l
+
+
+@pytest.mark.parametrize("w,h,mips", [(2048, 1024, True), (260, 124, True)])
+def test_compress_pinned_and_pageable_buffers_agree(ctx, w, h, mips):
+    """Pageable caller memory (numpy arrays, what the C++ drop-in passes) is staged through the library's pinned buffers
+    with its copy pool; pinned memory is used in place.  Same blocks either way, also with only one side pinned."""
+    import ctypes as C
+
+    import torch
+    img = synth.make_texture(w, h, 1, seed=5 * w + h)
+    plan, want = ctx.compress(img, capi.MODE_BC7, mips)  # pageable in, pageable out
+    for pin_in, pin_out in [(True, True), (True, False), (False, True)]:
+        src = torch.from_numpy(np.ascontiguousarray(img))
+        src = src.pin_memory() if pin_in else src
+        outs = [torch.zeros((int(plan.level_num_blocks[l]), 16), dtype=torch.uint8) for l in range(plan.num_levels)]
+        outs = [o.pin_memory() if pin_out else o for o in outs]
+        ptrs = (C.c_void_p * plan.num_levels)(*[o.data_ptr() for o in outs])
+        ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), w, h, 4, int(mips), None, ptrs))
+        for l in range(plan.num_levels):
+            assert np.array_equal(outs[l].numpy(), want[l]), (pin_in, pin_out, l)
