@@ -169,6 +169,48 @@ typedef struct vkt_bcn_source
 int vkt_bcn_cuda_compress_batch(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32_t num_sources, int generate_mipmaps,
                                 const vkt_bc7_params *params);
 
+/* ONE chain split over several PROCESSES, one GPU each (north_star: "independent block rows and mip levels
+ * shard across the 8 GPUs of one box by simple partitioning, with no NCCL collective, and results are gathered back over
+ * pinned async copies").  The reference shards a level into batches of four block rows for its thread pool
+ * (src/texture_block_compression.cpp:107-139); here worker `rank` of `world` (a single-device context each) takes the
+ * block rows [rows * rank / world, rows * (rank + 1) / world) of every level that is large enough to slice, uploads only the
+ * source rows those reach through the filter taps (own rows + a halo of a few rows per level, recomputed instead of
+ * exchanged), and writes its blocks at their final position inside level_blocks[l] -- so when `pixels` and `level_blocks`
+ * are one buffer shared by the workers (POSIX shared memory registered with vkt_bcn_cuda_host_register, or any pinned
+ * mapping), every GPU's copy engine gathers straight into the caller's contiguous level arrays.  Levels too small to slice
+ * (fewer than 128 pixel rows or 4 block rows per worker) are finished by worker 0; it continues the chain from the last
+ * sliced level, whose rows the other workers leave in `handover` (host memory all workers see, `handover_bytes` large):
+ *     every worker:  vkt_bcn_cuda_compress_shard_begin(...)   queue own slices; returns once own rows are in `handover`
+ *     the caller:    a barrier over the workers (any mechanism; no data moves)
+ *     every worker:  vkt_bcn_cuda_compress_shard_end(...)     worker 0 queues the small levels; all wait for their work
+ * The union of the workers' blocks is byte-identical to vkt_bcn_cuda_compress on one device.  `pixels` / `level_blocks[l]`
+ * may be host or device memory as for vkt_bcn_cuda_compress (a device-resident source on the worker's own GPU is read in
+ * place).  begin and end must be called from the same host thread with the same arguments; no other call may be made on
+ * the context in between. */
+typedef struct vkt_bcn_shard_plan
+{
+    uint32_t num_levels;
+    uint32_t sliced_levels;  /* levels [0, sliced_levels) are split by block rows over `workers` (0: worker 0 does everything) */
+    uint32_t workers;        /* workers that take part (1 if the image is too small to slice) */
+    uint64_t handover_bytes; /* size of the hand-over buffer (0: none needed) */
+} vkt_bcn_shard_plan;
+int vkt_bcn_cuda_compress_shard_plan(uint32_t width, uint32_t height, int generate_mipmaps, uint32_t world, vkt_bcn_shard_plan *out);
+/* block rows [*first_block_row, *end_block_row) of `level` that worker `rank` encodes (empty for levels it has no part in) */
+int vkt_bcn_cuda_compress_shard_rows(uint32_t width, uint32_t height, int generate_mipmaps, uint32_t rank, uint32_t world,
+                                     uint32_t level, uint32_t *first_block_row, uint32_t *end_block_row);
+int vkt_bcn_cuda_compress_shard_begin(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
+                                      uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, uint32_t rank,
+                                      uint32_t world, void *const *level_blocks, void *handover);
+int vkt_bcn_cuda_compress_shard_end(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
+                                    uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, uint32_t rank,
+                                    uint32_t world, void *const *level_blocks, void *handover);
+
+/* Page-lock caller memory (cudaHostRegister, portable) so that copies from / to it run asynchronously at full link speed:
+ * what a loader does once for a long-lived decode buffer or for the shared result buffer of a sharded chain.  Pageable
+ * memory works everywhere without this (the library stages it), only slower. */
+int vkt_bcn_cuda_host_register(vkt_bcn_ctx *ctx, void *ptr, size_t bytes);
+int vkt_bcn_cuda_host_unregister(vkt_bcn_ctx *ctx, void *ptr);
+
 /* Counters for the measurement harness: kernels launched / bytes copied by this context since creation. */
 typedef struct vkt_bcn_stats
 {

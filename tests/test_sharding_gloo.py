@@ -23,6 +23,23 @@ def test_plan_covers_every_block_once(w, h, world):
         assert (seen == 1).all(), (l, lw, lh)
 
 
+@pytest.mark.parametrize("w,h,world", [(16384, 16384, 8), (8192, 8192, 8), (8192, 8192, 2), (4096, 4096, 4), (1000, 520, 2), (64, 64, 2),
+                                        (16384, 16384, 1), (2050, 2046, 3), (4, 4, 8)])
+def test_c_abi_shard_plan_matches_the_python_mirror(cuda_lib, w, h, world):
+    """vkt_bcn_cuda_compress_shard_plan / _rows (what a process-per-GPU driver asks the library) == sharding.py."""
+    from vierkant_b200 import capi
+    dims = sharding.chain_dims(w, h)
+    m, workers = sharding.chain_split([lh for _, lh in dims], world)
+    sp = capi.shard_plan(w, h, True, world)
+    assert (sp.num_levels, sp.workers) == (len(dims), workers)
+    assert sp.sliced_levels == (m if workers > 1 else 0)
+    tail = workers > 1 and m < len(dims)
+    assert sp.handover_bytes == (dims[m - 1][0] * dims[m - 1][1] * 4 if tail else 0)
+    for r in range(world):
+        for l, e in enumerate(sharding.shard_plan(w, h, r, world)):
+            assert capi.shard_rows(w, h, True, r, world, l) == e["rows"]
+
+
 @pytest.fixture(scope="module")
 def emul_lib():
     import ctypes as C

@@ -54,6 +54,11 @@ class Source(C.Structure):
                 ("level_blocks", C.POINTER(C.c_void_p))]
 
 
+class ShardPlan(C.Structure):
+    """vkt_bcn_shard_plan"""
+    _fields_ = [("num_levels", C.c_uint32), ("sliced_levels", C.c_uint32), ("workers", C.c_uint32), ("handover_bytes", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
@@ -64,6 +69,8 @@ EXPORTS = [
     "vkt_bcn_cuda_encode_batch", "vkt_bcn_cuda_encode_bc7_device", "vkt_bcn_cuda_encode_bc5_device",
     "vkt_bcn_cuda_resize_u8", "vkt_bcn_cuda_compress_plan", "vkt_bcn_cuda_compress", "vkt_bcn_cuda_get_stats",
     "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device", "vkt_bcn_cuda_compress_batch",
+    "vkt_bcn_cuda_compress_shard_plan", "vkt_bcn_cuda_compress_shard_rows", "vkt_bcn_cuda_compress_shard_begin",
+    "vkt_bcn_cuda_compress_shard_end", "vkt_bcn_cuda_host_register", "vkt_bcn_cuda_host_unregister",
 ]
 
 _lib = None
@@ -99,6 +106,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.vkt_bcn_cuda_compress_plan.argtypes = [u32, u32, C.c_int, C.POINTER(Plan)]
     L.vkt_bcn_cuda_compress.argtypes = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), C.POINTER(vp)]
     L.vkt_bcn_cuda_compress_batch.argtypes = [vp, C.POINTER(Source), u32, C.c_int, C.POINTER(Bc7Params)]
+    L.vkt_bcn_cuda_compress_shard_plan.argtypes = [u32, u32, C.c_int, u32, C.POINTER(ShardPlan)]
+    L.vkt_bcn_cuda_compress_shard_rows.argtypes = [u32, u32, C.c_int, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    shard_args = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), u32, u32, C.POINTER(vp), vp]
+    L.vkt_bcn_cuda_compress_shard_begin.argtypes = shard_args
+    L.vkt_bcn_cuda_compress_shard_end.argtypes = shard_args
+    L.vkt_bcn_cuda_host_register.argtypes = [vp, vp, C.c_size_t]
+    L.vkt_bcn_cuda_host_unregister.argtypes = [vp, vp]
     L.vkt_bcn_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.vkt_bcn_cuda_measure_issue_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     if path == _build.CUDA_SO:
@@ -128,6 +142,22 @@ def compress_plan(width: int, height: int, generate_mipmaps: bool) -> Plan:
     if rc:
         raise BcnError(rc, "invalid size")
     return plan
+
+
+def shard_plan(width: int, height: int, generate_mipmaps: bool, world: int) -> ShardPlan:
+    """vkt_bcn_cuda_compress_shard_plan: how ONE chain is split over `world` single-GPU workers."""
+    sp = ShardPlan()
+    if load_library().vkt_bcn_cuda_compress_shard_plan(width, height, int(generate_mipmaps), world, C.byref(sp)):
+        raise BcnError(ERR_INVALID, "invalid shard plan arguments")
+    return sp
+
+
+def shard_rows(width: int, height: int, generate_mipmaps: bool, rank: int, world: int, level: int) -> tuple[int, int]:
+    """Block rows [r0, r1) of `level` that worker `rank` of `world` encodes."""
+    r0, r1 = C.c_uint32(), C.c_uint32()
+    if load_library().vkt_bcn_cuda_compress_shard_rows(width, height, int(generate_mipmaps), rank, world, level, C.byref(r0), C.byref(r1)):
+        raise BcnError(ERR_INVALID, "invalid shard rows arguments")
+    return int(r0.value), int(r1.value)
 
 
 def device_count() -> int:
@@ -248,6 +278,28 @@ class BcnContext:
         pp = C.byref(params) if params is not None else None
         self._check(self.lib.vkt_bcn_cuda_compress(self.handle, mode, _ptr(img), w, h, c, int(generate_mipmaps), pp, ptrs))
         return plan, levels
+
+    def compress_shard_begin(self, mode: int, pixels, width: int, height: int, comps: int, generate_mipmaps: bool,
+                             params: Bc7Params | None, rank: int, world: int, level_ptrs, handover) -> None:
+        """Worker `rank` of `world`: queue this GPU's row slices of ONE chain (vkt_bcn_cuda_compress_shard_begin).  `level_ptrs` is
+        a (c_void_p * levels) array of the (shared) level buffers, `handover` the shared hand-over buffer (or None)."""
+        pp = C.byref(params) if params is not None else None
+        self._check(self.lib.vkt_bcn_cuda_compress_shard_begin(self.handle, mode, _ptr(pixels), width, height, comps, int(generate_mipmaps),
+                                                               pp, rank, world, level_ptrs, None if handover is None else _ptr(handover)))
+
+    def compress_shard_end(self, mode: int, pixels, width: int, height: int, comps: int, generate_mipmaps: bool,
+                           params: Bc7Params | None, rank: int, world: int, level_ptrs, handover) -> None:
+        pp = C.byref(params) if params is not None else None
+        self._check(self.lib.vkt_bcn_cuda_compress_shard_end(self.handle, mode, _ptr(pixels), width, height, comps, int(generate_mipmaps),
+                                                             pp, rank, world, level_ptrs, None if handover is None else _ptr(handover)))
+
+    def host_register(self, buf) -> None:
+        """cudaHostRegister (portable) of a numpy array / torch tensor the caller keeps alive."""
+        n = buf.nbytes if hasattr(buf, "nbytes") else buf.numel() * buf.element_size()
+        self._check(self.lib.vkt_bcn_cuda_host_register(self.handle, _ptr(buf), n))
+
+    def host_unregister(self, buf) -> None:
+        self._check(self.lib.vkt_bcn_cuda_host_unregister(self.handle, _ptr(buf)))
 
     def compress_batch(self, imgs: list, modes: int | list = MODE_BC7, generate_mipmaps: bool = True,
                        params: Bc7Params | None = None) -> list[list[np.ndarray]]:

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -295,6 +296,7 @@ struct DeviceSlot
         size_t bytes;
     };
     std::vector<PendingCopy> pending;
+    bool src_in_place = false;// the running chain reads its source where the caller keeps it (device memory of this device)
     std::mutex mtx;
 };
 
@@ -313,11 +315,14 @@ struct vkt_bcn_ctx
     std::unique_ptr<vkt::CopyPool> copy_pool;// made on first use (a caller with pageable buffers)
     std::mutex copy_pool_mtx;
     size_t stage_cap = 0;
+    std::unique_lock<std::mutex> shard_lock;// slot 0's mutex, held from compress_shard_begin to compress_shard_end
+    std::atomic<bool> shard_open{false};
 };
 
 namespace vkt
 {
 static thread_local std::string t_create_error;
+static thread_local std::string t_last_error;// vkt_bcn_cuda_last_error's answer outlives other threads' failures
 
 static int fail(vkt_bcn_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -377,6 +382,18 @@ static bool is_pageable_host(const void *p)
         return true;
     }
     return a.type == cudaMemoryTypeUnregistered;
+}
+
+// device memory of device `dev` (an allocation of this process or an imported one)?
+static bool device_pointer_on(const void *p, int dev)
+{
+    cudaPointerAttributes a;
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice && a.device == dev;
 }
 
 static CopyPool &copy_pool(vkt_bcn_ctx *ctx)
@@ -580,9 +597,36 @@ static cudaError_t init_slot(vkt::DeviceSlot *s, const vkt::Bc7Tables &host_tabl
     return e;
 }
 
+static void destroy_slot(vkt::DeviceSlot *s);
+
 #include "resize_core.cuh"
 
 using namespace vkt;
+
+// streams, events, buffers and cached tables of one slot (also a partly initialised one: every member starts out null)
+static void destroy_slot(vkt::DeviceSlot *s)
+{
+    if(cudaSetDevice(s->device) == cudaSuccess)
+    {
+        for(cudaStream_t st: {s->stream, s->stream3, s->stream4, s->stream5, s->stream6, s->stream2})
+        {
+            if(st)
+            {
+                cudaStreamSynchronize(st);
+                cudaStreamDestroy(st);
+            }
+        }
+        for(cudaEvent_t ev: s->event_pool) { cudaEventDestroy(ev); }
+        cudaFree(s->d_tables);
+        cudaFree(s->d_in);
+        cudaFree(s->d_out);
+        cudaFree(s->d_tmp);
+        if(s->h_in) { cudaFreeHost(s->h_in); }
+        if(s->h_out) { cudaFreeHost(s->h_out); }
+        delete s->axis_cache;// frees the cached resize tables
+    }
+    delete s;
+}
 
 // ================================================================================================ C ABI
 extern "C" {
@@ -661,39 +705,7 @@ void vkt_bcn_cuda_destroy(vkt_bcn_ctx *ctx)
     if(ctx->h_stage) { cudaFreeHost(ctx->h_stage); }
     std::vector<vkt::DeviceSlot *> all(ctx->slots);
     all.insert(all.end(), ctx->slots2.begin(), ctx->slots2.end());
-    for(auto *s: all)
-    {
-        if(cudaSetDevice(s->device) == cudaSuccess)
-        {
-            if(s->stream)
-            {
-                cudaStreamSynchronize(s->stream);
-                cudaStreamDestroy(s->stream);
-            }
-            for(cudaStream_t st: {s->stream3, s->stream4, s->stream5, s->stream6})
-            {
-                if(st)
-                {
-                    cudaStreamSynchronize(st);
-                    cudaStreamDestroy(st);
-                }
-            }
-            if(s->stream2)
-            {
-                cudaStreamSynchronize(s->stream2);
-                cudaStreamDestroy(s->stream2);
-            }
-            for(cudaEvent_t ev: s->event_pool) { cudaEventDestroy(ev); }
-            cudaFree(s->d_tables);
-            cudaFree(s->d_in);
-            cudaFree(s->d_out);
-            cudaFree(s->d_tmp);
-            if(s->h_in) { cudaFreeHost(s->h_in); }
-            if(s->h_out) { cudaFreeHost(s->h_out); }
-            delete s->axis_cache;// frees the cached resize tables
-        }
-        delete s;
-    }
+    for(auto *s: all) { destroy_slot(s); }
     delete ctx;
 }
 
@@ -702,7 +714,13 @@ int vkt_bcn_cuda_num_devices(const vkt_bcn_ctx *ctx) { return ctx ? int(ctx->slo
 const char *vkt_bcn_cuda_last_error(const vkt_bcn_ctx *ctx)
 {
     if(!ctx) { return t_create_error.c_str(); }
-    return ctx->last_error.c_str();
+    {
+        // copied under the lock into a per-thread buffer: another thread's failure may reassign ctx->last_error at any time
+        auto *c = const_cast<vkt_bcn_ctx *>(ctx);
+        std::lock_guard<std::mutex> g(c->err_mtx);
+        t_last_error = c->last_error;
+    }
+    return t_last_error.c_str();
 }
 
 int vkt_bcn_cuda_get_stats(const vkt_bcn_ctx *ctx, vkt_bcn_stats *out)
@@ -777,7 +795,11 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
     {
         DeviceSlot *s = ctx->slots[g];
         if(plan[g].empty()) { continue; }
-        VKT_CUDA(ctx, cudaSetDevice(s->device));
+        if(cudaSetDevice(s->device) != cudaSuccess)
+        {
+            rc = fail(ctx, VKT_BCN_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+            break;
+        }
         if((rc = ensure(ctx, &s->d_in, &s->in_cap, in_need[g]))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_need[g]))) { break; }
         // pageable images / block buffers are staged through pinned mirrors of d_in / d_out (see host_copy.h)
@@ -787,9 +809,80 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         if(page_out && (rc = ensure_pinned(ctx, &s->h_out, &s->h_out_cap, out_need[g]))) { break; }
         s->pending.clear(), s->events_used = 0;
     }
-    // queue group by group, round-robin over devices so that all PCIe links start early
+    // queue group by group, round-robin over devices so that all PCIe links start early.  A failure inside queue_group
+    // only ends the queueing: the synchronise loop below still runs, so no copy into / out of the caller's buffers is in
+    // flight when this call reports the error.
     constexpr uint64_t kGroupBlocks = 1u << 20;
     std::vector<size_t> next(G, 0), group_no(G, 0);
+    auto queue_group = [&](uint32_t g) -> int {
+        DeviceSlot *s = ctx->slots[g];
+        VKT_CUDA(ctx, cudaSetDevice(s->device));
+        cudaStream_t st = (group_no[g]++ & 1) ? s->stream2 : s->stream;
+        const size_t first = next[g];
+        uint64_t blocks = 0;
+        std::vector<DevImage> dev;
+        while(next[g] < plan[g].size() && dev.size() < kBc7MaxImages && (dev.empty() || blocks < kGroupBlocks))
+        {
+            const Piece &p = plan[g][next[g]++];
+            const vkt_bcn_image &img = images[p.img];
+            const uint32_t stride = img.row_stride_bytes ? img.row_stride_bytes : img.width * img.comps;
+            const uint32_t rows = p.row1 - p.row0;
+            const size_t row_bytes = size_t(img.width) * img.comps;
+            uint8_t *d_in = static_cast<uint8_t *>(s->d_in) + p.in_off;
+            // the device copy is tightly packed
+            const uint8_t *from = img.pixels + size_t(p.row0) * 4 * stride;
+            if(pageable_in[p.img])
+            {
+                uint8_t *staged = static_cast<uint8_t *>(s->h_in) + p.in_off;
+                if(stride == row_bytes) { copy_pool(ctx).copy(staged, from, size_t(rows) * 4 * row_bytes); }
+                else
+                {
+                    for(size_t r = 0; r < size_t(rows) * 4; ++r) { memcpy(staged + r * row_bytes, from + r * stride, row_bytes); }
+                }
+                VKT_CUDA(ctx, cudaMemcpyAsync(d_in, staged, size_t(rows) * 4 * row_bytes, cudaMemcpyHostToDevice, st));
+            }
+            else
+            {
+                VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, from, stride, row_bytes, size_t(rows) * 4, cudaMemcpyDefault, st));
+            }
+            dev.push_back({d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), static_cast<uint8_t *>(s->d_out) + p.out_off});
+            blocks += uint64_t(rows) * (img.width / 4);
+            count(ctx, 0, size_t(rows) * 4 * row_bytes, 0);
+        }
+        int r = VKT_BCN_OK;
+        if(mode == VKT_BCN_MODE_BC7) { r = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, st); }
+        else
+        {
+            for(const DevImage &d: dev)
+            {
+                if((r = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, st))) { break; }
+            }
+        }
+        for(size_t k = first; k < next[g] && !r; ++k)
+        {
+            const Piece &p = plan[g][k];
+            const vkt_bcn_image &img = images[p.img];
+            const size_t row_blk = size_t(img.width / 4) * 16, bytes = size_t(p.row1 - p.row0) * row_blk;
+            uint8_t *user = static_cast<uint8_t *>(img.out_blocks) + size_t(p.row0) * row_blk;
+            if(pageable_out[p.img])
+            {
+                uint8_t *staged = static_cast<uint8_t *>(s->h_out) + p.out_off;
+                VKT_CUDA(ctx, cudaMemcpyAsync(staged, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDeviceToHost, st));
+                if(s->events_used == s->event_pool.size())
+                {
+                    cudaEvent_t fresh;
+                    VKT_CUDA(ctx, cudaEventCreateWithFlags(&fresh, cudaEventDisableTiming));
+                    s->event_pool.push_back(fresh);
+                }
+                cudaEvent_t landed = s->event_pool[s->events_used++];
+                VKT_CUDA(ctx, cudaEventRecord(landed, st));
+                s->pending.push_back({landed, staged, user, bytes});
+            }
+            else { VKT_CUDA(ctx, cudaMemcpyAsync(user, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDefault, st)); }
+            count(ctx, 0, 0, bytes);
+        }
+        return r;
+    };
     bool more = !rc;
     while(more && !rc)
     {
@@ -797,71 +890,7 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         for(uint32_t g = 0; g < G && !rc; ++g)
         {
             if(next[g] >= plan[g].size()) { continue; }
-            DeviceSlot *s = ctx->slots[g];
-            VKT_CUDA(ctx, cudaSetDevice(s->device));
-            cudaStream_t st = (group_no[g]++ & 1) ? s->stream2 : s->stream;
-            const size_t first = next[g];
-            uint64_t blocks = 0;
-            std::vector<DevImage> dev;
-            while(next[g] < plan[g].size() && dev.size() < kBc7MaxImages && (dev.empty() || blocks < kGroupBlocks))
-            {
-                const Piece &p = plan[g][next[g]++];
-                const vkt_bcn_image &img = images[p.img];
-                const uint32_t stride = img.row_stride_bytes ? img.row_stride_bytes : img.width * img.comps;
-                const uint32_t rows = p.row1 - p.row0;
-                const size_t row_bytes = size_t(img.width) * img.comps;
-                uint8_t *d_in = static_cast<uint8_t *>(s->d_in) + p.in_off;
-                // the device copy is tightly packed
-                const uint8_t *from = img.pixels + size_t(p.row0) * 4 * stride;
-                if(pageable_in[p.img])
-                {
-                    uint8_t *staged = static_cast<uint8_t *>(s->h_in) + p.in_off;
-                    if(stride == row_bytes) { copy_pool(ctx).copy(staged, from, size_t(rows) * 4 * row_bytes); }
-                    else
-                    {
-                        for(size_t r = 0; r < size_t(rows) * 4; ++r) { memcpy(staged + r * row_bytes, from + r * stride, row_bytes); }
-                    }
-                    VKT_CUDA(ctx, cudaMemcpyAsync(d_in, staged, size_t(rows) * 4 * row_bytes, cudaMemcpyHostToDevice, st));
-                }
-                else
-                {
-                    VKT_CUDA(ctx, cudaMemcpy2DAsync(d_in, row_bytes, from, stride, row_bytes, size_t(rows) * 4, cudaMemcpyDefault, st));
-                }
-                dev.push_back({d_in, img.width, rows * 4, img.comps, uint32_t(row_bytes), static_cast<uint8_t *>(s->d_out) + p.out_off});
-                blocks += uint64_t(rows) * (img.width / 4);
-                count(ctx, 0, size_t(rows) * 4 * row_bytes, 0);
-            }
-            if(mode == VKT_BCN_MODE_BC7) { rc = launch_bc7_batch(ctx, s, dev.data(), uint32_t(dev.size()), params, st); }
-            else
-            {
-                for(const DevImage &d: dev)
-                {
-                    if((rc = launch_bc5(ctx, s, d.d_px, d.w, d.h, d.comps, d.stride, d.d_out, st))) { break; }
-                }
-            }
-            for(size_t k = first; k < next[g] && !rc; ++k)
-            {
-                const Piece &p = plan[g][k];
-                const vkt_bcn_image &img = images[p.img];
-                const size_t row_blk = size_t(img.width / 4) * 16, bytes = size_t(p.row1 - p.row0) * row_blk;
-                uint8_t *user = static_cast<uint8_t *>(img.out_blocks) + size_t(p.row0) * row_blk;
-                if(pageable_out[p.img])
-                {
-                    uint8_t *staged = static_cast<uint8_t *>(s->h_out) + p.out_off;
-                    VKT_CUDA(ctx, cudaMemcpyAsync(staged, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDeviceToHost, st));
-                    if(s->events_used == s->event_pool.size())
-                    {
-                        cudaEvent_t fresh;
-                        VKT_CUDA(ctx, cudaEventCreateWithFlags(&fresh, cudaEventDisableTiming));
-                        s->event_pool.push_back(fresh);
-                    }
-                    cudaEvent_t landed = s->event_pool[s->events_used++];
-                    VKT_CUDA(ctx, cudaEventRecord(landed, st));
-                    s->pending.push_back({landed, staged, user, bytes});
-                }
-                else { VKT_CUDA(ctx, cudaMemcpyAsync(user, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDefault, st)); }
-                count(ctx, 0, 0, bytes);
-            }
+            rc = queue_group(g);
             more = more || next[g] < plan[g].size();
         }
     }
@@ -874,8 +903,8 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         for(const DeviceSlot::PendingCopy &pc: s->pending)// blocks staged for pageable destinations, each as soon as it has landed
         {
             const cudaError_t e1 = cudaEventSynchronize(pc.ready);
-            if(e1 == cudaSuccess) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
-            else if(e == cudaSuccess) { e = e1; }
+            if(e1 == cudaSuccess && !rc) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
+            else if(e1 != cudaSuccess && e == cudaSuccess) { e = e1; }
         }
         s->pending.clear();
         const cudaError_t e0 = cudaStreamSynchronize(s->stream), e2 = cudaStreamSynchronize(s->stream2);
@@ -1035,6 +1064,96 @@ int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
 {
     if(!ctx) { return VKT_BCN_ERR_INVALID; }
     return compress_chain(ctx, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks);
+}
+
+// ---- one chain split over several processes (one GPU each) ------------------------------------------------------------
+int vkt_bcn_cuda_compress_shard_plan(uint32_t width, uint32_t height, int generate_mipmaps, uint32_t world, vkt_bcn_shard_plan *out)
+{
+    vkt_bcn_plan plan;
+    if(!out || world == 0 || vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps, &plan)) { return VKT_BCN_ERR_INVALID; }
+    const ChainSplit split = chain_split(plan.level_height, plan.num_levels, world);
+    std::memset(out, 0, sizeof(*out));
+    out->num_levels = plan.num_levels, out->sliced_levels = split.devices > 1 ? split.sliced : 0, out->workers = split.devices;
+    out->handover_bytes = split.tail() ? uint64_t(plan.level_width[split.sliced - 1]) * plan.level_height[split.sliced - 1] * 4u : 0u;
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_compress_shard_rows(uint32_t width, uint32_t height, int generate_mipmaps, uint32_t rank, uint32_t world, uint32_t level,
+                                     uint32_t *first_block_row, uint32_t *end_block_row)
+{
+    vkt_bcn_plan plan;
+    if(!first_block_row || !end_block_row || world == 0 || rank >= world || vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps, &plan))
+    {
+        return VKT_BCN_ERR_INVALID;
+    }
+    if(level >= plan.num_levels) { return VKT_BCN_ERR_INVALID; }
+    const ChainSplit split = chain_split(plan.level_height, plan.num_levels, world);
+    const uint32_t rows = plan.level_height[level] / 4;
+    if(split.devices > 1 && level < split.sliced)
+    {
+        *first_block_row = uint32_t(uint64_t(rows) * rank / split.devices), *end_block_row = uint32_t(uint64_t(rows) * (rank + 1) / split.devices);
+    }
+    else { *first_block_row = rank == 0 ? 0u : rows, *end_block_row = rows; }
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_compress_shard_begin(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                                      int generate_mipmaps, const vkt_bc7_params *params, uint32_t rank, uint32_t world,
+                                      void *const *level_blocks, void *handover)
+{
+    if(!ctx) { return VKT_BCN_ERR_INVALID; }
+    if(ctx->slots.size() != 1) { return fail(ctx, VKT_BCN_ERR_INVALID, "a process shard runs on a single-device context (%zu devices)", ctx->slots.size()); }
+    // (checked before the mutex is touched: the thread that opened a shard still holds it)
+    if(ctx->shard_open) { return fail(ctx, VKT_BCN_ERR_INVALID, "compress_shard_begin without the compress_shard_end of the previous one"); }
+    std::unique_lock<std::mutex> lock(ctx->slots[0]->mtx);
+    ChainShard sh;
+    sh.rank = rank, sh.world = world, sh.handover = static_cast<uint8_t *>(handover), sh.phase = 1;
+    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, nullptr, &sh);
+    if(!rc && sh.handed_over)
+    {
+        // the caller's barrier must mean "every worker's rows are in the hand-over buffer"
+        const cudaError_t e = cudaEventSynchronize(sh.handed_over);
+        if(e != cudaSuccess) { rc = fail(ctx, VKT_BCN_ERR_CUDA, "hand-over copy failed: %s", cudaGetErrorString(e)); }
+    }
+    if(rc)
+    {
+        chain_wait(ctx, ctx->slots);// nothing of a failed call stays in flight
+        return rc;
+    }
+    ctx->shard_lock = std::move(lock), ctx->shard_open = true;
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_compress_shard_end(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                                    int generate_mipmaps, const vkt_bc7_params *params, uint32_t rank, uint32_t world,
+                                    void *const *level_blocks, void *handover)
+{
+    if(!ctx) { return VKT_BCN_ERR_INVALID; }
+    if(!ctx->shard_open || !ctx->shard_lock.owns_lock()) { return fail(ctx, VKT_BCN_ERR_INVALID, "compress_shard_end without compress_shard_begin"); }
+    ChainShard sh;
+    sh.rank = rank, sh.world = world, sh.handover = static_cast<uint8_t *>(handover), sh.phase = 2;
+    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, nullptr, &sh);
+    const int rw = chain_wait(ctx, ctx->slots);
+    if(!rc) { rc = rw; }
+    ctx->shard_open = false;
+    ctx->shard_lock.unlock();
+    ctx->shard_lock = std::unique_lock<std::mutex>();
+    return rc;
+}
+
+int vkt_bcn_cuda_host_register(vkt_bcn_ctx *ctx, void *ptr, size_t bytes)
+{
+    if(!ctx || !ptr || !bytes) { return VKT_BCN_ERR_INVALID; }
+    VKT_CUDA(ctx, cudaSetDevice(ctx->slots[0]->device));
+    VKT_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_host_unregister(vkt_bcn_ctx *ctx, void *ptr)
+{
+    if(!ctx || !ptr) { return VKT_BCN_ERR_INVALID; }
+    VKT_CUDA(ctx, cudaHostUnregister(ptr));
+    return VKT_BCN_OK;
 }
 
 }// extern "C"

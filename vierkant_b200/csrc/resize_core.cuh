@@ -150,28 +150,38 @@ __global__ void __launch_bounds__(256) resize_v_kernel(const float *__restrict__
 }// namespace vkt
 
 // per-slot cache of axis tables (keyed by in/out size); lives beside the DeviceSlot, guarded by the slot mutex
+// Entries are shared: a caller keeps the shared_ptr for as long as it (or a kernel it queued) reads the tables, so an
+// eviction can never free tables that are still referenced (DeviceAxis's destructor calls cudaFree, which waits for the
+// device).
+using vkt_axis_ptr = std::shared_ptr<const vkt::DeviceAxis>;
 struct vkt_axis_cache
 {
-    std::map<std::pair<int, int>, std::unique_ptr<vkt::DeviceAxis>> axes;
+    std::map<std::pair<int, int>, vkt_axis_ptr> axes;
 };
 
 namespace vkt
 {
 
-static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, const DeviceAxis **res)
+constexpr size_t kAxisCacheEntries = 256;
+
+static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, vkt_axis_ptr *res)
 {
     if(!s->axis_cache) { s->axis_cache = new vkt_axis_cache; }
     auto &m = s->axis_cache->axes;
     auto it = m.find({in, out});
     if(it != m.end())
     {
-        *res = it->second.get();
+        *res = it->second;
         return VKT_BCN_OK;
     }
-    if(m.size() > 256) { m.clear(); }
+    if(m.size() >= kAxisCacheEntries)
+    {
+        // drop what nobody holds; entries the running call still references stay (and stay valid)
+        for(auto e = m.begin(); e != m.end();) { e = (e->second.use_count() == 1) ? m.erase(e) : std::next(e); }
+    }
     ResizeAxis h;
     h.build(in, out);
-    auto d = std::make_unique<DeviceAxis>();
+    auto d = std::make_shared<DeviceAxis>();
     d->in_size = in, d->out_size = out;
     const size_t n = h.idx.size();
     VKT_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d->d_start), (size_t(out) + 1) * sizeof(int)));
@@ -194,7 +204,7 @@ static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, const Devi
         if(h.start[size_t(o)] == h.start[size_t(o) + 1]) { lo = hi = 0; }
         d->first_in[size_t(o)] = lo, d->last_in[size_t(o)] = hi;
     }
-    *res = d.get();
+    *res = d;
     m[{in, out}] = std::move(d);
     return VKT_BCN_OK;
 }
@@ -207,7 +217,7 @@ static int resize_device(vkt_bcn_ctx *ctx, DeviceSlot *s, const uint8_t *d_src, 
                          uint32_t ow, uint32_t oh, cudaStream_t stream, uint32_t out_y0 = 0, uint32_t out_y1 = 0)
 {
     if(out_y1 == 0) { out_y1 = oh; }
-    const DeviceAxis *ax = nullptr, *ay = nullptr;
+    vkt_axis_ptr ax, ay;
     int rc = get_axis(ctx, s, int(w), int(ow), &ax);
     if(rc) { return rc; }
     if((rc = get_axis(ctx, s, int(h), int(oh), &ay))) { return rc; }
@@ -279,9 +289,22 @@ static int resize_host(vkt_bcn_ctx *ctx, const uint8_t *pixels, uint32_t w, uint
 // the copies that read / write them are issued with cudaMemcpyDefault (unified addressing), so a caller that owns a device
 // buffer -- e.g. a Vulkan staging or image buffer imported with cudaImportExternalMemory -- gets its
 // blocks without a trip through the host.
+// One process per GPU (vkt_bcn_cuda_compress_shard_begin / _end): this context is worker `rank` of `world` workers that split
+// ONE chain exactly as the devices of a multi-device context do (chain_plan.h).  phase 1 queues the worker's row slices of the
+// sliced levels (and, for rank > 0, the copy of its rows of the last sliced level into `handover`, host memory every worker
+// sees); phase 2, on rank 0 after the callers have met at a barrier, continues the chain from `handover` through the small
+// levels.  No device-to-device traffic and no collective: the hand-over is a few hundred KB per worker.
+struct ChainShard
+{
+    uint32_t rank = 0, world = 1;
+    uint8_t *handover = nullptr;
+    int phase = 1;
+    cudaEvent_t handed_over = nullptr;// out (phase 1, rank > 0): fires when this worker's rows have landed in `handover`
+};
+
 static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots, uint32_t mode, const uint8_t *pixels, uint32_t width,
                          uint32_t height, uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks,
-                         std::vector<std::pair<cudaEvent_t, std::string>> *marks_out)
+                         std::vector<std::pair<cudaEvent_t, std::string>> *marks_out, ChainShard *shard = nullptr)
 {
     if(mode != VKT_BCN_MODE_BC7 && mode != VKT_BCN_MODE_BC5) { return fail(ctx, VKT_BCN_ERR_INVALID, "unknown mode %u", mode); }
     if(!pixels || !level_blocks || !width || !height) { return fail(ctx, VKT_BCN_ERR_INVALID, "null buffer or empty image"); }
@@ -300,7 +323,8 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         const int rc = bc7_prepare_params(params ? params : &def, &kp);
         if(rc) { return fail(ctx, rc, rc == VKT_BCN_ERR_UNSUPPORTED ? "unsupported bc7 parameters" : "invalid bc7 parameters"); }
     }
-    const uint32_t G = uint32_t(slots.size());
+    const uint32_t G = shard ? shard->world : uint32_t(slots.size());
+    if(shard && (shard->rank >= shard->world || slots.size() != 1)) { return fail(ctx, VKT_BCN_ERR_INVALID, "bad shard (rank %u of %u)", shard->rank, shard->world); }
     const size_t src_bytes = size_t(width) * height * comps;
     // Pageable caller memory (what the C++ drop-in passes: a malloc'ed image in, std::vector blocks out) is staged through
     // pinned buffers of the slot with the copy pool (host_copy.h); pinned and device memory is used in place.
@@ -385,7 +409,13 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     };
     std::vector<cudaEvent_t> gathered(Geff, nullptr);
     size_t gather_row_bytes = 0;
-    if(tail)
+    uint8_t *h_gather = shard ? shard->handover : nullptr;
+    if(tail && shard)
+    {
+        gather_row_bytes = size_t(plan.level_width[M - 1]) * comps;
+        if(!h_gather) { return fail(ctx, VKT_BCN_ERR_INVALID, "this chain needs a hand-over buffer (vkt_bcn_cuda_compress_shard_plan)"); }
+    }
+    else if(tail)
     {
         gather_row_bytes = size_t(plan.level_width[M - 1]) * comps;
         const size_t need = gather_row_bytes * plan.level_height[M - 1];
@@ -396,6 +426,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             VKT_CUDA(ctx, cudaHostAlloc(&ctx->h_stage, need, cudaHostAllocPortable));
             ctx->stage_cap = need;
         }
+        h_gather = static_cast<uint8_t *>(ctx->h_stage);
     }
     // blocks at d_ptr (inside slot sl's d_out) -> bytes [off, off + bytes) of the caller's level l, queued on st
     auto fetch = [&](DeviceSlot *sl, uint32_t l, size_t off, const void *d_ptr, size_t bytes, cudaStream_t st) -> int {
@@ -415,16 +446,21 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     };
     for(uint32_t g = 0; g < Geff && !rc; ++g)
     {
-        DeviceSlot *s = slots[g];
+        if(shard && (g != shard->rank || shard->phase != 1)) { continue; }// a process shard: this worker's slices only
+        DeviceSlot *s = slots[shard ? 0 : g];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
         ev_slot = s, s->events_used = 0;
-        if((rc = ensure(ctx, &s->d_in, &s->in_cap, align_up(src_bytes, 256) + lvl_total))) { break; }
+        // a source that already lives on this device is read in place (no copy, no room for a copy)
+        const bool src_in_place = device_pointer_on(pixels, s->device);
+        s->src_in_place = src_in_place;
+        if((rc = ensure(ctx, &s->d_in, &s->in_cap, (src_in_place ? 0 : align_up(src_bytes, 256)) + lvl_total))) { break; }
         if((rc = ensure(ctx, &s->d_out, &s->out_cap, out_total))) { break; }
-        uint8_t *d_src = static_cast<uint8_t *>(s->d_in), *d_lvl = d_src + align_up(src_bytes, 256);
+        uint8_t *d_src = src_in_place ? const_cast<uint8_t *>(pixels) : static_cast<uint8_t *>(s->d_in);
+        uint8_t *d_lvl = static_cast<uint8_t *>(s->d_in) + (src_in_place ? 0 : align_up(src_bytes, 256));
         s->pending.clear();
         if(any_stage_out && (rc = ensure_pinned(ctx, &s->h_out, &s->h_out_cap, out_total))) { break; }
         // vertical tap ranges of every sliced level: ay[l] maps rows of level l-1 (l == 0: the source) to rows of level l
-        std::vector<const DeviceAxis *> ay(M, nullptr);
+        std::vector<vkt_axis_ptr> ay(M);
         for(uint32_t l = 0; l < M && !rc; ++l) { rc = get_axis(ctx, s, int(l ? plan.level_height[l - 1] : height), int(plan.level_height[l]), &ay[l]); }
         if(rc) { break; }
         // own[l]: this device's block rows of level l;  need[l]: the pixel rows of level l it has to produce (own rows
@@ -460,7 +496,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             const uint32_t lo = rows.first, hi = rows.second;
             // subtract what is already there
             std::vector<std::pair<uint32_t, uint32_t>> todo;
-            if(lo < hi) { todo.push_back({lo, hi}); }
+            if(lo < hi && !src_in_place) { todo.push_back({lo, hi}); }
             for(const auto &iv: have)
             {
                 std::vector<std::pair<uint32_t, uint32_t>> next;
@@ -610,10 +646,11 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         {
             // this device's rows of level M-1 -> the pinned gather buffer (device 0 continues the chain from there)
             const size_t off = size_t(own[M - 1].first) * 4 * gather_row_bytes, bytes = size_t(own[M - 1].second - own[M - 1].first) * 4 * gather_row_bytes;
-            VKT_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t *>(ctx->h_stage) + off, d_lvl + lvl_off[M - 1] + off, bytes, cudaMemcpyDeviceToHost, s->stream));
+            VKT_CUDA(ctx, cudaMemcpyAsync(h_gather + off, d_lvl + lvl_off[M - 1] + off, bytes, cudaMemcpyDeviceToHost, s->stream));
             count(ctx, 0, 0, bytes);
             VKT_CUDA(ctx, new_event(&gathered[g]));
             VKT_CUDA(ctx, cudaEventRecord(gathered[g], s->stream));
+            if(shard) { shard->handed_over = gathered[g]; }
         }
         auto encode_and_fetch = [&]() -> int {
             if(!dev.empty())
@@ -645,19 +682,20 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         };
         if((rc = encode_and_fetch())) { break; }
     }
-    if(tail && !rc)
+    if(tail && !rc && (!shard || (shard->phase == 2 && shard->rank == 0)))
     {
         // small levels [M, L) on device 0: wait for every device's rows of level M-1, fetch them, continue the chain
+        // (a process shard: the workers' barrier between phase 1 and phase 2 was that wait)
         DeviceSlot *s = slots[0];
         VKT_CUDA(ctx, cudaSetDevice(s->device));
         ev_slot = s;
-        uint8_t *d_lvl = static_cast<uint8_t *>(s->d_in) + align_up(src_bytes, 256);
-        for(uint32_t g = 1; g < Geff; ++g) { VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, gathered[g], 0)); }
+        uint8_t *d_lvl = static_cast<uint8_t *>(s->d_in) + (s->src_in_place ? 0 : align_up(src_bytes, 256));
+        for(uint32_t g = 1; g < Geff && !shard; ++g) { VKT_CUDA(ctx, cudaStreamWaitEvent(s->stream, gathered[g], 0)); }
         {
             // rows of the other devices only (device 0's own rows are in place and may still be read by its encode kernels)
             const size_t off = size_t(plan.level_height[M - 1] / 4 * 1 / Geff) * 4 * gather_row_bytes;
             const size_t total = gather_row_bytes * plan.level_height[M - 1];
-            VKT_CUDA(ctx, cudaMemcpyAsync(d_lvl + lvl_off[M - 1] + off, static_cast<uint8_t *>(ctx->h_stage) + off, total - off, cudaMemcpyHostToDevice, s->stream));
+            VKT_CUDA(ctx, cudaMemcpyAsync(d_lvl + lvl_off[M - 1] + off, h_gather + off, total - off, cudaMemcpyHostToDevice, s->stream));
             count(ctx, 0, total - off, 0);
         }
         std::vector<DevImage> dev;
@@ -753,9 +791,15 @@ static int compress_many(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32
     {
         auto *s = new DeviceSlot;
         s->device = ctx->slots[ctx->slots2.size()]->device;
-        ctx->slots2.push_back(s);
         const cudaError_t e = init_slot(s, ctx->host_tables);
-        if(e != cudaSuccess) { return fail(ctx, VKT_BCN_ERR_CUDA, "second lane of device %d: %s", s->device, cudaGetErrorString(e)); }
+        if(e != cudaSuccess)
+        {
+            // a half-made lane must not be found by the next call
+            const int dev = s->device;
+            destroy_slot(s);
+            return fail(ctx, VKT_BCN_ERR_CUDA, "second lane of device %d: %s", dev, cudaGetErrorString(e));
+        }
+        ctx->slots2.push_back(s);
     }
     std::vector<std::vector<DeviceSlot *>> lanes;// lane k: device k % G, set k / G
     for(size_t k = 0; k < 2 * G; ++k) { lanes.push_back({(k < G) ? ctx->slots[k] : ctx->slots2[k - G]}); }
