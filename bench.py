@@ -18,9 +18,14 @@ data path; weak scaling) and `value` is the whole-job pixel rate over the max-ov
            reference's compress() with stbir on the host cores) is compared with.
   roofline     : ALU/issue-slot bound: algorithmic lane-ops per launch / kernel time vs a peak
                  microbenchmarked in this run; HBM GB/s alongside (informational).
-  cpu_baseline : the reference (oracle/_ref, unmodified sources) or the C port, on a bounded sample, on rank 0 at N=1.
-  parity       : the reference's output of that sample compared block by block with the same call on the GPU (untimed).
+  cpu_baseline : the reference (oracle/_ref, unmodified sources) on the host cores, rank 0 at N=1: vierkant::bcn::compress of
+                 the SAME chain with all host threads (value), one thread on a 1024^2 crop (n1), and bc7enc_compress_block
+                 alone over the pre-filtered levels with a row partition over the threads (blocks_only).
+  parity       : the reference's blocks of the whole chain compared block by block with the e2e call's (untimed).
   e2e_pageable : the e2e call once more with pageable host buffers, as the C++ drop-in passes them (informational).
+  e2e_dropin   : integration/texture_block_compression_cuda.cpp's vierkant::bcn::compress() itself (crocore image in,
+                 compress_result_t with freshly allocated std::vectors out), compiled against the reference's headers.
+  strong       : ONE 16384^2 (C5) and ONE 8192^2 (C3) chain sharded by block rows over the N ranks -- bench_strong.py.
 """
 from __future__ import annotations
 
@@ -168,66 +173,86 @@ def bind_near_gpu(local: int):
         return f"not bound ({type(e).__name__})"
 
 
-def cpu_baseline_sample(threads: int | None = None, reps: int = 2):
-    """The reference's CPU path on a bounded sample: vierkant::bcn::compress() of the top-left 2048x2048 crop of the
-    workload texture with mipmaps, delegate = thread pool with all host threads (as model::compress_textures does).
-    Returns (Mpixel/s over all levels, dict)."""
+def load_ops_per_pixel(workload: str, default: float):
+    """Algorithmic scalar ops per pixel of a config (SURVEY.md 8d op model x gcov event rates of the reference on this
+    config's own inputs): profiles/gcov_ops.json, written by tools/gcov_ops.py.  Falls back to the survey's figure."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gcov_ops.json")) as f:
+            e = json.load(f)["configs"][workload]
+        return float(e["ops_per_pixel"]), f"profiles/gcov_ops.json ({e['blocks']} blocks of {e['input']}: {e['ops_per_block']:.0f} ops/block)"
+    except Exception:
+        return default, "SURVEY.md App. D (gcov on unfiltered 1024^2 inputs)"
+
+
+def reference_oracle():
+    """(oracle, kind): the unmodified reference compiled in place (oracle/_ref) or, where it is absent, the C port."""
     from oracle import pyoracle
-    crop = np.ascontiguousarray(synth.make_texture(2048, 2048, KIND))
-    npix = sum(w * h for w, h in chain_dims(2048))
     if pyoracle.RefOracle.available():
-        ref = pyoracle.RefOracle()
-        cores = threads or ref.hardware_concurrency()
-        best = None
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            result = ref.compress(crop, 1, True, cores)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        levels = result["levels"]
-        kind = "reference"
-        what = ("vierkant::bcn::compress (unmodified reference, oracle/_ref) of a 2048x2048 crop + 10 mip levels "
-                f"(5.59 Mpixel), ThreadPoolClassic delegate with {cores} threads, stbir included, best of {reps}")
-    else:
-        pyoracle.build("port")
-        port = pyoracle.PortOracle()
-        cores = threads or (os.cpu_count() or 1)
-        tiles = synth.to_blocks(crop)
-        npix = 2048 * 2048
-        best = None
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            port.encode_blocks(tiles, None, threads=cores)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        kind = "port"
-        levels = None
-        what = f"C port of bc7enc_compress_block over the 262144 blocks of a 2048x2048 crop, {cores} threads, best of {reps}"
-    return npix / best * 1e-6, {"cores": cores, "kind": kind, "sample": what, "seconds": best}, crop, levels
+        return pyoracle.RefOracle(), "reference"
+    pyoracle.build("port")
+    return pyoracle.PortOracle(), "port"
+
+
+def reference_chain(oracle, kind: str, tex: np.ndarray, cores: int):
+    """vierkant::bcn::compress(image, BC7, generate_mipmaps) of the reference with a ThreadPoolClassic(cores) delegate, as
+    model::compress_textures calls it (src/model/model_loading.cpp:110-118); the C port mirrors it where _ref is absent."""
+    if kind == "reference":
+        return oracle.compress(tex, 1, True, cores)["levels"]
+    return oracle.compress(tex, 1, True, threads=cores)["levels"]
+
+
+def cpu_baseline_full(tex: np.ndarray, filtered_levels: list, reps: int = 2):
+    """The reference's CPU path on the host cores for the bench's own chain: all threads, one thread
+    (bounded: a 1024^2 crop + mips) and blocks only.  Returns (dict for the JSON line, reference blocks per level)."""
+    oracle, kind = reference_oracle()
+    cores = oracle.hardware_concurrency() if kind == "reference" else (os.cpu_count() or 1)
+    h, w, _ = tex.shape
+    npix = sum(a * b for a, b in chain_dims(w))
+    best, levels = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        levels = reference_chain(oracle, kind, tex, cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    crop = np.ascontiguousarray(tex[:1024, :1024])
+    t0 = time.perf_counter()
+    reference_chain(oracle, kind, crop, 1)
+    n1_s = time.perf_counter() - t0
+    n1_pix = sum(a * b for a, b in chain_dims(1024))
+    tiles = [synth.to_blocks(np.ascontiguousarray(lv)) for lv in filtered_levels]
+    t0 = time.perf_counter()
+    blocks_only = [oracle.encode_blocks(t, None, threads=cores) for t in tiles]
+    bo_s = time.perf_counter() - t0
+    same = all(np.array_equal(a, b) for a, b in zip(blocks_only, levels))
+    name = "vierkant::bcn::compress (unmodified reference, oracle/_ref)" if kind == "reference" else "C port of vierkant::bcn::compress (oracle/*.c)"
+    info = {"value": npix / best * 1e-6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+            "sample": f"{name} of the whole {w}x{h} chain ({npix * 1e-6:.2f} Mpixel, stbir included), thread-pool delegate with {cores} threads, best of {reps}",
+            "seconds": best,
+            "n1": {"value": n1_pix / n1_s * 1e-6, "unit": "Mpixel/s", "cores": 1,
+                   "sample": f"the same call, no delegate (one thread), on the top-left 1024x1024 crop + mips ({n1_pix * 1e-6:.2f} Mpixel)"},
+            "blocks_only": {"value": npix / bo_s * 1e-6, "unit": "Mpixel/s", "cores": cores,
+                            "sample": "bc7enc_compress_block over every block of the pre-filtered levels (the GPU path's own stbir-exact levels), "
+                                      f"row partition over {cores} threads; blocks equal compress()'s: {same}"}}
+    return info, levels
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation on the SAME config -- each step is vierkant::bcn::compress
+    of the whole workload chain, all host threads (stbir included, as the reference does)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    from oracle import pyoracle
-    crop = np.ascontiguousarray(synth.make_texture(2048, 2048, KIND))
-    npix = sum(w * h for w, h in chain_dims(2048))
-    if pyoracle.RefOracle.available():
-        ref = pyoracle.RefOracle()
-        cores = ref.hardware_concurrency()
-        step = lambda: ref.compress(crop, 1, True, cores)
-        kind = "reference"
-    else:
-        pyoracle.build("port")
-        port = pyoracle.PortOracle()
-        cores = os.cpu_count() or 1
-        tiles = synth.to_blocks(crop)
-        npix = 2048 * 2048
-        step = lambda: port.encode_blocks(tiles, None, threads=cores)
-        kind = "port"
+    wl = WORKLOADS[args.workload]
+    base = args.base or wl["base"]
+    if wl["params"]:
+        raise SystemExit("--impl reference: vierkant::bcn::compress() has no parameter argument; configs with non-default bc7enc parameters "
+                         "are covered by bench.py's strong.*.parity.reference.cpu_blocks_only")
+    tex = np.ascontiguousarray(synth.make_texture(base, base, wl["kind"], seed=0xB200))
+    npix = sum(w * h for w, h in chain_dims(base))
+    oracle, kind = reference_oracle()
+    cores = oracle.hardware_concurrency() if kind == "reference" else (os.cpu_count() or 1)
+    step = lambda: reference_chain(oracle, kind, tex, cores)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -235,14 +260,16 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = npix * steps / dt * 1e-6
-    sample = ("each step = vierkant::bcn::compress of the top-left 2048x2048 crop of the workload texture + its 10 mip "
-              "levels (5.59 Mpixel; stbir included as in the reference), ThreadPoolClassic delegate, all host threads"
-              if kind == "reference" else "each step = C port over the 262144 blocks of a 2048x2048 crop, all host threads")
+    sample = (f"each step = vierkant::bcn::compress of the whole workload chain ({base}x{base} + mips, {npix * 1e-6:.2f} Mpixel; stbir included "
+              f"as in the reference), ThreadPoolClassic delegate, {cores} host threads" if kind == "reference" else
+              f"each step = the C port of vierkant::bcn::compress over the whole workload chain, {cores} host threads")
+    workload = wl["name"] if base == wl["base"] else wl["name"].replace(f"{wl['base']}x{wl['base']}", f"{base}x{base}")
     print(json.dumps({
         "impl": "reference", "metric": "bc7_encode_mpixel_per_s", "value": v, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32+f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": workload, "levels": len(chain_dims(base)), "mpixel_per_step": npix * 1e-6, "sample": sample,
+                   "same_config": True},
         "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -257,6 +284,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default c2 = configs[1])")
     ap.add_argument("--base", type=int, default=None, help="override the workload's level-0 size (experiments only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", default="c5,c3", help="strong-scaling configs to run after the headline (comma list of c5, c3; '' = none)")
+    ap.add_argument("--strong-base", type=int, default=None, help="override the strong configs' level-0 size (experiments only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -301,17 +330,22 @@ def main():
     npix = sum(w * h for w, h in dims) * NTEX
     nblocks = sum((w // 4) * (h // 4) for w, h in dims) * NTEX
 
-    # synthetic level images (every level generated at its own size by the App. C generator; per-rank seeds)
-    host_levels = []   # [rotation][level] pinned uint8 tensors
+    # Inputs.  Source textures come from the App. C generator (per-rank seeds).  The resident arm (`value`) encodes the
+    # stbir-filtered levels of those chains: made here, untimed, by the library's own bit-exact resize
+    # (vkt_bcn_cuda_resize_u8, the path tests/test_chain_gpu.py pins to the reference) -- level 0 is the 1:1 Mitchell pass of
+    # the source, level l the 2:1 pass of level l-1, exactly as compress() derives them.
+    host_src = []      # [texture] pinned source image (what the e2e call is given)
+    host_levels = []   # [texture][level] filtered level images (numpy)
     dev_levels = []
     for r in range(ROTATE * NTEX):
-        hl, dl = [], []
         kind = KIND if NTEX == 1 else (1 if (r % 4 == 3) else 0)
+        img = synth.make_texture(dims[0][0], dims[0][1], kind, seed=0xB200 + 16 * rank + r)
+        host_src.append(torch.from_numpy(img).pin_memory())
+        hl, dl, prev = [], [], img
         for (w, h) in dims:
-            img = synth.make_texture(w, h, kind, seed=0xB200 + 16 * rank + r)
-            t = torch.from_numpy(img).pin_memory()
-            hl.append(t)
-            dl.append(t.to(dev, non_blocking=True))
+            prev = ctx.resize_u8(prev, w, h)
+            hl.append(prev)
+            dl.append(torch.from_numpy(prev).to(dev))
         host_levels.append(hl)
         dev_levels.append(dl)
     dev_out = [[torch.empty(((w // 4) * (h // 4), 16), dtype=torch.uint8, device=dev) for (w, h) in dims] for _ in range(NTEX)]
@@ -343,14 +377,14 @@ def main():
         for r in range(ROTATE):
             arr = (capi.Source * NTEX)()
             for j in range(NTEX):
-                arr[j] = capi.Source(host_levels[r * NTEX + j][0].data_ptr(), dims[0][0], dims[0][1], 4, capi.MODE_BC7, out_ptrs_b[j])
+                arr[j] = capi.Source(host_src[r * NTEX + j].data_ptr(), dims[0][0], dims[0][1], 4, capi.MODE_BC7, out_ptrs_b[j])
             batch_srcs.append(arr)
 
     def step_e2e(i):
         if batch_srcs is not None:
             ctx._check(ctx.lib.vkt_bcn_cuda_compress_batch(ctx.handle, batch_srcs[i % ROTATE], NTEX, 1, C.byref(params)))
             return
-        src = host_levels[i % ROTATE][0]  # the level-0 texture is the source image of the chain
+        src = host_src[i % ROTATE]
         ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), dims[0][0], dims[0][1], 4, 1,
                                                  C.byref(params), out_ptrs))
 
@@ -408,7 +442,7 @@ def main():
     # informational, N = 1 / single-texture workloads only, outside every other timed region
     pageable_ms = None
     if world == 1 and batch_srcs is None and dims[0][0] <= 8192:
-        p_src = torch.from_numpy(host_levels[0][0].numpy().copy())  # plain (unpinned) host memory
+        p_src = torch.from_numpy(host_src[0].numpy().copy())  # plain (unpinned) host memory
         p_outs = [torch.empty_like(o, pin_memory=False) for o in host_out]
         p_ptrs = (C.c_void_p * len(p_outs))(*[o.data_ptr() for o in p_outs])
         for i in range(args.warmup + args.steps):
@@ -418,10 +452,56 @@ def main():
                                                      C.byref(params), p_ptrs))
         pageable_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
+    # the C++ drop-in itself: integration/texture_block_compression_cuda.cpp's vierkant::bcn::compress(), compiled against the
+    # reference's headers -- a crocore image wrapping a malloc'ed buffer in, a compress_result_t with freshly allocated
+    # std::vector<block_t> levels out (allocation, zero fill and release of the result are part of every call, as in vierkant)
+    dropin = None
+    dropin_so = os.path.join(ROOT, "integration", "_build", "libvkt_dropin_test.so")
+    if world == 1 and batch_srcs is None and os.path.exists(dropin_so):
+        try:
+            os.environ["VIERKANT_BCN_CUDA_DEVICES"] = str(local)  # the drop-in's process-wide context: this GPU only
+            D = C.CDLL(dropin_so)
+            D.dropin_compress.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+            D.dropin_compress.restype = C.c_void_p
+            D.dropin_result_free.argtypes = [C.c_void_p]
+            D.dropin_result_duration_ms.argtypes, D.dropin_result_duration_ms.restype = [C.c_void_p], C.c_int64
+            D.dropin_result_level_data.argtypes, D.dropin_result_level_data.restype = [C.c_void_p, C.c_uint32], C.c_void_p
+            srcs = [host_src[r].numpy().copy() for r in range(ROTATE)]
+            last = None
+            for i in range(args.warmup + args.steps):
+                if i == args.warmup:
+                    t0 = time.perf_counter()
+                r = D.dropin_compress(srcs[i % ROTATE].ctypes.data, dims[0][0], dims[0][1], 4, capi.MODE_BC7, 1)
+                if i + 1 == args.warmup + args.steps:
+                    last = r
+                else:
+                    D.dropin_result_free(r)
+            d_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            n0 = (dims[0][0] // 4) * (dims[0][1] // 4)
+            lvl0 = np.frombuffer((C.c_uint8 * (16 * n0)).from_address(D.dropin_result_level_data(last, 0)), dtype=np.uint8).reshape(n0, 16).copy()
+            dropin = {"value": npix / (d_ms * 1e-3) * 1e-6, "unit": "Mpixel/s", "ms_per_step": d_ms, "duration_field_ms": int(D.dropin_result_duration_ms(last)),
+                      "level0": lvl0, "texture": (args.warmup + args.steps - 1) % ROTATE,
+                      "api": "vierkant::bcn::compress(compress_info_t) of integration/texture_block_compression_cuda.cpp (libvkt_dropin_test.so): "
+                             "pageable crocore::Image in, compress_result_t (new std::vector<block_t> per level) out, result released each step"}
+            D.dropin_result_free(last)
+        except Exception as e:  # noqa: BLE001
+            dropin = {"value": None, "error": repr(e)}
+
     tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = float(tms[0]), float(tms[1])
+
+    # ---- ONE chain sharded over the ranks (north_star: 16K-class strong scaling) ----------------------------------------
+    strong = {}
+    for name in [x for x in args.strong.split(",") if x]:
+        import bench_strong
+        if name not in bench_strong.STRONG:
+            continue
+        # release the headline's buffers first?  They are small (0.6 GB); the C5 chain needs ~4 GB of the 180 GB per GPU.
+        rep = bench_strong.run_strong(name, ctx, rank, world, dev, args, dist, base=args.strong_base, check=not args.no_cpu_baseline)
+        if rank == 0:
+            strong[name] = rep
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -438,6 +518,7 @@ def main():
         except Exception:
             probe = None
         l0_pix = dims[0][0] * dims[0][1]
+        OPS_PER_PIXEL, ops_source = load_ops_per_pixel(args.workload, OPS_PER_PIXEL)
         achieved = l0_pix * OPS_PER_PIXEL / (kernel_ms * 1e-3)
         line = {
             "metric": "bc7_encode_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
@@ -446,6 +527,7 @@ def main():
             "config": {"workload": WORKLOAD, "levels": len(dims), "textures_per_gpu": NTEX, "blocks_per_step_per_gpu": nblocks,
                        "mpixel_per_step_per_gpu": npix * 1e-6, "partitioning": f"{world * NTEX} independent texture chains, {NTEX} per GPU, no collective",
                        "l2": f"{ROTATE * NTEX} textures rotated: {ROTATE * npix * 4 / 1e6:.0f} MB of inputs > 126 MB L2",
+                       "resident_inputs": "the stbir-filtered levels of each texture's chain (level 0 = 1:1 Mitchell pass, level l from level l-1), made untimed by vkt_bcn_cuda_resize_u8",
                        "params": wl["params_name"], "host_affinity": affinity},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": (b1["h2d_bytes"] - b0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": (b1["d2h_bytes"] - b0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
@@ -464,7 +546,7 @@ def main():
                          "traffic": NCU_TRAFFIC_BYTES if (args.workload == "c2" and base == wl["base"]) else None,
                          "traffic_source": "profiles/r1_ww_ncu_summary.txt (72.81 MB read + 5.72 MB written; algorithmic 83.9 MB, part of the writes still in L2)",
                          "kernel": f"bc7_encode_kernel<perceptual> launch set on level 0 ({base}x{base})", "kernel_ms": kernel_ms,
-                         "ops_per_pixel": OPS_PER_PIXEL,
+                         "ops_per_pixel": OPS_PER_PIXEL, "ops_source": ops_source,
                          "peak_source": f"{props.multi_processor_count} SMs x 4 x 32 lanes x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peak_src} clock)",
                          "sm_mhz_during_run": sm_mhz,
                          "issue_probe_tlaneops": None if probe is None else probe * 1e-12,
@@ -472,20 +554,34 @@ def main():
                          "hbm": {"achieved_gbs": l0_pix * BYTES_PER_PIXEL / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": f"informational, {peak_src}"}},
         }
-        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
+        lvl0 = None
+        if dropin is not None:
+            lvl0 = dropin.pop("level0", None)
+            line["e2e_dropin"] = dropin
+        if strong:
+            line["strong"] = strong
+        if world == 1 and not args.no_cpu_baseline and NTEX == 1 and not wl["params"] and dims[0][0] <= 4096:
             try:
-                v, info, crop, ref_levels = cpu_baseline_sample()
-                line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", **info}
-                if ref_levels is not None:
-                    # the reference's output of the baseline sample doubles as an in-run parity check (untimed): the same crop
-                    # through the same C-ABI call the e2e figure times, compared block by block
-                    _, ours = ctx.compress(crop, capi.MODE_BC7, True, params)
-                    total = sum(int(a.shape[0]) for a in ref_levels)
-                    bad = sum(int((np.asarray(a).reshape(-1, 16) != np.asarray(b).reshape(-1, 16)).any(axis=1).sum())
-                              for a, b in zip(ours, ref_levels))
-                    line["parity"] = {"against": "unmodified reference (oracle/_ref), vierkant::bcn::compress of the cpu_baseline sample",
-                                      "levels": len(ref_levels), "blocks": total, "mismatched_blocks": bad,
-                                      "bit_exact": bool(bad == 0 and len(ours) == len(ref_levels))}
+                tex0 = host_src[0].numpy()
+                info, ref_levels = cpu_baseline_full(tex0, host_levels[0])
+                line["cpu_baseline"] = info
+                # the reference's blocks of the WHOLE chain double as the in-run parity check (untimed): the same texture through
+                # the same C-ABI call the e2e figure times, compared block by block
+                _, ours = ctx.compress(tex0, capi.MODE_BC7, True, params)
+                total = sum(int(a.shape[0]) for a in ref_levels)
+                bad = sum(int((np.asarray(a).reshape(-1, 16) != np.asarray(b).reshape(-1, 16)).any(axis=1).sum())
+                          for a, b in zip(ours, ref_levels))
+                line["parity"] = {"against": ("unmodified reference (oracle/_ref)" if info["kind"] == "reference" else "C port (oracle/*.c)") +
+                                             ", vierkant::bcn::compress of the whole workload chain",
+                                  "levels": len(ref_levels), "blocks": total, "mismatched_blocks": bad,
+                                  "bit_exact": bool(bad == 0 and len(ours) == len(ref_levels))}
+                # the resident arm's outputs (rotation 0 was encoded last at steps % ROTATE == 1 ... re-encode to be sure)
+                ctx.encode_batch_device(capi.MODE_BC7, dev_batches[0], params, 0, stream)
+                torch.cuda.synchronize()
+                rbad = sum(int((o.cpu().numpy() != np.asarray(b).reshape(-1, 16)).any(axis=1).sum()) for o, b in zip(dev_out[0], ref_levels))
+                line["parity"]["resident_arm_mismatched_blocks"] = rbad
+                if "e2e_dropin" in line and lvl0 is not None and line["e2e_dropin"].get("texture") == 0:
+                    line["e2e_dropin"]["level0_matches_reference"] = bool(np.array_equal(lvl0, ref_levels[0]))
             except Exception as e:  # the baseline must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line))

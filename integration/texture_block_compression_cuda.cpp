@@ -16,10 +16,12 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include <vierkant/texture_block_compression.hpp>
 
@@ -37,7 +39,20 @@ struct cuda_context_t
     vkt_bcn_ctx *ctx = nullptr;
     cuda_context_t()
     {
-        if(vkt_bcn_cuda_create(&ctx, nullptr, 0) != VKT_BCN_OK)
+        // VIERKANT_BCN_CUDA_DEVICES="0,2": restrict the encoder to these CUDA ordinals (default: every visible device)
+        std::vector<int> devices;
+        if(const char *e = std::getenv("VIERKANT_BCN_CUDA_DEVICES"))
+        {
+            for(const char *q = e; *q;)
+            {
+                char *end = nullptr;
+                const long v = std::strtol(q, &end, 10);
+                if(end == q) { break; }
+                devices.push_back(int(v));
+                q = (*end == ',') ? end + 1 : end;
+            }
+        }
+        if(vkt_bcn_cuda_create(&ctx, devices.empty() ? nullptr : devices.data(), int(devices.size())) != VKT_BCN_OK)
         {
             throw std::runtime_error(std::string("vierkant::bcn (CUDA): ") + vkt_bcn_cuda_last_error(nullptr));
         }
@@ -136,8 +151,17 @@ std::vector<compress_result_t> compress(std::span<const compress_info_t> compres
     {
         throw std::runtime_error(std::string("vierkant::bcn::compress (CUDA, batch): ") + vkt_bcn_cuda_last_error(context.ctx));
     }
-    auto elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - start_time);
-    for(auto &r: results) { r.duration = std::max(elapsed, std::chrono::milliseconds(1)); }// the batch's time: textures overlap
+    // model::compress_textures SUMS the results' durations for its "avg. Mpx/s" log (src/model/model_loading.cpp:119,135-138).
+    // The textures of a batch overlap on the device, so each result carries its pixel share of the batch's wall time -- the
+    // sum is the batch's time (never 0 per result: the reference's test asserts duration > 0 ms, tests/TestCompressionBC7.cpp:48).
+    const double elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start_time).count();
+    double total_px = 0.0;
+    for(const auto &r: results) { total_px += double(r.base_width) * r.base_height; }
+    for(auto &r: results)
+    {
+        const double share = total_px > 0.0 ? double(r.base_width) * r.base_height / total_px : 0.0;
+        r.duration = std::max(std::chrono::milliseconds(static_cast<int64_t>(elapsed_ms * share + 0.5)), std::chrono::milliseconds(1));
+    }
     return results;
 }
 

@@ -127,3 +127,18 @@ def test_port_compress_known_answer_1024(port_oracle, known):
     allb = np.concatenate(r["levels"])
     assert (len(r["levels"]), allb.shape[0]) == (e["levels"], e["blocks"])
     assert "%016x" % synth.fnv1a64_words(allb) == e["fnv1a64"]
+
+
+def test_slab_chain_equals_whole_image_resize(ref_oracle):
+    """oracle/slab.py: rows of a deep mip level from a chain of small band resizes == the reference's whole-image chain
+    (what lets bench.py and the GPU tests check 8K / 16K chains against the reference without filtering 1 GB on one core)."""
+    from oracle import slab
+    w = h = 512
+    img = synth.make_texture(w, h, 1, seed=31)
+    levels, prev = [], img
+    for l in range(5):
+        prev = ref_oracle.resize(prev, w >> l, h >> l)
+        levels.append(prev)
+    for level, y0, y1 in [(0, 0, 16), (0, 200, 264), (0, 496, 512), (1, 0, 8), (1, 100, 132), (2, 60, 76), (3, 0, 64), (4, 12, 20), (4, 28, 32)]:
+        got = slab.level_rows(ref_oracle, lambda a, b: img[a:b], w, h, level, y0, y1)
+        assert np.array_equal(got, levels[level][y0:y1]), (level, y0, y1)

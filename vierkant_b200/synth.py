@@ -6,6 +6,8 @@ PRNG: s = s*1664525 + 1013904223 (mod 2^32), draw = s >> 24, four draws per pixe
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 _A = 1664525
@@ -29,18 +31,35 @@ def _affine_powers(n: int):
     return a, c
 
 
-def make_texture(width: int, height: int, kind: int = 0, seed: int | None = None) -> np.ndarray:
-    """Return an (H, W, 4) uint8 texture.  kind 0 = opaque albedo-like, kind 1 = alpha gradients (right half)."""
+def _affine_pow(a: int, c: int, n: int) -> tuple[int, int]:
+    """(a, c) composed n times: x -> a x + c applied n times (mod 2^32), by repeated squaring."""
+    ra, rc = 1, 0
+    while n:
+        if n & 1:
+            ra, rc = (a * ra) & _M, (a * rc + c) & _M
+        a, c = (a * a) & _M, (a * c + c) & _M
+        n >>= 1
+    return ra, rc
+
+
+def make_texture(width: int, height: int, kind: int = 0, seed: int | None = None, rows: tuple[int, int] | None = None,
+                 out: np.ndarray | None = None) -> np.ndarray:
+    """Return an (H, W, 4) uint8 texture.  kind 0 = opaque albedo-like, kind 1 = alpha gradients (right half).
+    rows = (y0, y1): only those rows of the texture (the generator's state is jumped to row y0), returned as a
+    (y1 - y0, W, 4) array or written into `out` -- how several processes fill one shared image."""
     if seed is None:
         seed = 0xB200 + kind
     W, H = int(width), int(height)
     a_k, c_k = _affine_powers(4 * W)
     # affine map for a whole row (4W draws), to jump from row start to row start
     row_a, row_c = int(a_k[-1]), int(c_k[-1])
-    out = np.empty((H, W, 4), dtype=np.uint8)
+    y0, y1 = rows if rows is not None else (0, H)
+    full = out if out is not None else np.empty((y1 - y0, W, 4), dtype=np.uint8)
+    out = _RowView(full, y0)
     x = np.arange(W, dtype=np.int64)
-    s = seed & _M
-    for y in range(H):
+    ja, jc = _affine_pow(row_a, row_c, y0)
+    s = (ja * (seed & _M) + jc) & _M
+    for y in range(y0, y1):
         st = (a_k * np.uint64(s) + c_k) & np.uint64(_M)  # states after draws 1..4W
         draws = (st >> np.uint64(24)).astype(np.int64).reshape(W, 4)
         s = (row_a * s + row_c) & _M
@@ -62,7 +81,18 @@ def make_texture(width: int, height: int, kind: int = 0, seed: int | None = None
             grad = np.clip((2 * (x - W // 2) + y) * 255 // (W + H) + na % 9 - 4, 0, 255)
             a = np.where(((bx + by) & 7) == 0, (bx * 37 + by * 11) & 255, np.where(((bx ^ by) & 7) == 1, 0, grad))
             out[y, :, 3] = np.where(x < W // 2, 255, a)
-    return out
+    return full
+
+
+class _RowView:
+    """out[y, :, c] addressing of a row range stored from row y0 on."""
+
+    def __init__(self, arr: np.ndarray, y0: int):
+        self.arr, self.y0 = arr, y0
+
+    def __setitem__(self, key, value):
+        y, xs, c = key
+        self.arr[y - self.y0, xs, c] = value
 
 
 def to_blocks(img: np.ndarray) -> np.ndarray:
@@ -100,3 +130,42 @@ def checkerboard_4x4(comps: int = 4) -> np.ndarray:
                       0xFF000000, 0xFFFFFFFF, 0xFF000000, 0xFFFFFFFF], dtype="<u4")
     raw = words.view(np.uint8)
     return raw[: 16 * comps].reshape(4, 4, comps).copy()
+
+
+def _fill_job(args):
+    path, offset, W, H, kind, seed, a, b = args
+    m = np.memmap(path, dtype=np.uint8, mode="r+", offset=offset + a * W * 4, shape=(b - a, W, 4))
+    make_texture(W, H, kind, seed, rows=(a, b), out=m)
+    m.flush()
+    return b - a
+
+
+def fill_shared(path: str, offset: int, width: int, height: int, kind: int, seed: int | None, rows: tuple[int, int],
+                procs: int = 1) -> None:
+    """Rows [rows[0], rows[1]) of make_texture(width, height, kind, seed) written into the file mapping `path` (a
+    hostshare.SharedBuffer) at byte `offset` + row * width * 4, by `procs` child processes (the generator is GIL-bound
+    numpy; the children are plain `python -m vierkant_b200.synth` runs, independent of the caller's __main__).  How the
+    workers of a sharded job fill one shared source image, each its own rows."""
+    import subprocess
+    import sys
+    y0, y1 = rows
+    procs = max(1, min(procs, (y1 - y0 + 63) // 64))
+    if seed is None:
+        seed = 0xB200 + kind
+    cuts = [y0 + (y1 - y0) * k // procs for k in range(procs + 1)]
+    jobs = [(path, offset, width, height, kind, seed, a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    if procs == 1:
+        for j in jobs:
+            _fill_job(j)
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    children = [subprocess.Popen([sys.executable, "-m", "vierkant_b200.synth", *map(str, j)], cwd=root) for j in jobs]
+    bad = [c.args for c in children if c.wait(timeout=900) != 0]
+    if bad:
+        raise RuntimeError(f"fill_shared: {len(bad)} generator processes failed")
+
+
+if __name__ == "__main__":  # python -m vierkant_b200.synth <path> <offset> <W> <H> <kind> <seed> <row0> <row1>
+    import sys
+    _a = sys.argv[1:]
+    _fill_job((_a[0], *map(int, _a[1:8])))
