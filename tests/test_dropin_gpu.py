@@ -120,3 +120,30 @@ def test_dropin_batch_overload_matches_single_calls():
                 assert np.array_equal(np.frombuffer(buf, dtype=np.uint8).reshape(n, 16), ref)
         finally:
             L.dropin_result_free(r)
+
+
+REF_GTEST = os.path.join(ROOT, "integration", "_build", "ref_gtest_bc7")
+REF_GTEST_CASES = ["CompressionBC5.", "  basic", "CompressionBC7.", "  basic", "  missing_alpha", "  mips", "  odd_size"]
+
+
+def test_reference_gtest_binary_lists_the_reference_cases():
+    """CPU-only: the reference's tests/TestCompressionBC7.cpp, compiled unmodified against the drop-in (integration/Makefile),
+    carries exactly the reference's five cases (no compute: --gtest_list_tests)."""
+    import subprocess
+    if not os.path.exists(REF_GTEST):
+        pytest.skip("integration/_build/ref_gtest_bc7 not built (needs the reference tree)")
+    out = subprocess.run([REF_GTEST, "--gtest_list_tests"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert [l.rstrip() for l in out.stdout.splitlines() if l.strip() and not l.startswith("Running main()")] == REF_GTEST_CASES
+
+
+@pytest.mark.gpu
+def test_reference_gtest_passes_against_the_dropin():
+    """The reference's own contract test (tests/TestCompressionBC7.cpp:59-131), unmodified source, googletest as vendored by the
+    reference, vierkant::bcn::compress() = the CUDA drop-in: all five cases must pass on the GPU."""
+    import subprocess
+    if not os.path.exists(REF_GTEST):
+        pytest.skip("integration/_build/ref_gtest_bc7 not built (needs the reference tree)")
+    out = subprocess.run([REF_GTEST], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "[  PASSED  ] 5 tests." in out.stdout
