@@ -253,6 +253,18 @@ def run_strong(cfg_name: str, ctx: capi.BcnContext, rank: int, world: int, dev, 
                                  if int(sc.sp.workers) > 1 else "one rank encodes the whole chain"),
                 "timing": "CUDA events around K lockstep chains (every call waits for its own GPU work), max with the host clock, max over ranks",
             }
+            try:  # ALU roofline of the whole job: gcov-pinned ops per pixel x pixel rate / (N x issue peak)
+                import json
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gcov_ops.json")) as f:
+                    opp = float(json.load(f)["configs"][cfg_name]["ops_per_pixel"])
+                props = torch.cuda.get_device_properties(dev)
+                peak = props.multi_processor_count * 4 * 32 * 1965.0e6
+                report["roofline"] = {"bound": "alu", "ops_per_pixel": opp, "ops_source": "profiles/gcov_ops.json",
+                                      "achieved": value * 1e6 * opp * 1e-12, "peak": world * peak * 1e-12, "unit": "Tlane-op/s",
+                                      "frac": value * 1e6 * opp / (world * peak),
+                                      "peak_source": f"{world} x {props.multi_processor_count} SMs x 4 x 32 lanes x 1965 MHz"}
+            except Exception:  # noqa: BLE001
+                pass
             if n1 is not None:
                 n1v, n1e = npix / n1["ms_resident"] * 1e-3, npix / n1["ms_e2e"] * 1e-3
                 report["n1"] = {"value": n1v, "e2e": n1e, "ms_per_step": n1["ms_resident"], "e2e_ms_per_step": n1["ms_e2e"],
