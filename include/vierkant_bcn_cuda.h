@@ -153,6 +153,18 @@ int vkt_bcn_cuda_compress_plan(uint32_t width, uint32_t height, int generate_mip
 int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
                           uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks);
 
+/* vkt_bcn_cuda_compress for a caller that allocates its result per call -- vierkant::bcn::compress() returns a fresh
+ * compress_result_t whose levels are std::vector<block_t> (include/vierkant/texture_block_compression.hpp:27-44;
+ * src/texture_block_compression.cpp:88-96 sizes them before the first block is encoded).  Here alloc_level(user, level, bytes) is
+ * called -- once per level, level 0 first, never concurrently, from a helper thread of the library -- while the calling thread
+ * queues the chain and the GPU already works, so the allocation and zero fill of the result (22 MB of fresh pages for a 4096^2
+ * chain) overlap the upload and the kernels instead of preceding them.  It returns host memory of `bytes` bytes that stays valid until the call returns; the blocks are handed over
+ * as their downloads land.  A null return aborts the call with VKT_BCN_ERR_OOM (nothing is left in flight). */
+typedef void *(*vkt_bcn_alloc_fn)(void *user, uint32_t level, size_t bytes);
+int vkt_bcn_cuda_compress_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height,
+                                uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, vkt_bcn_alloc_fn alloc_level,
+                                void *user);
+
 /* Several textures, each with its whole chain, in one call -- what model::compress_textures does texture by texture
  * (src/model/model_loading.cpp:96-118).  Every device of the context works on two textures at a time
  * (two sets of streams and buffers), so the upload and resizes of the next texture run under the encode kernels of the

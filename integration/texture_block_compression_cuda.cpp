@@ -89,18 +89,20 @@ compress_result_t compress(const compress_info_t &compress_info)
     ret.base_width = plan.base_width;
     ret.base_height = plan.base_height;
     ret.levels.resize(plan.num_levels);
-    void *level_ptrs[16] = {};
-    for(uint32_t l = 0; l < plan.num_levels; ++l)
-    {
-        ret.levels[l].resize(plan.level_num_blocks[l]);
-        level_ptrs[l] = ret.levels[l].data();
-    }
     static_assert(sizeof(block_t) == 16, "block_t is the 16-byte BCn block");
 
+    // The levels' storage is allocated by this callback, which the library calls once the whole chain is queued on the GPU:
+    // std::vector::resize maps and zero-fills the pages while the upload and the kernels already run (the reference sizes
+    // the vectors up front, src/texture_block_compression.cpp:88-96 -- in front of the first upload that is pure latency).
+    auto alloc_level = [](void *user, uint32_t level, size_t bytes) -> void * {
+        auto &levels = *static_cast<std::vector<std::vector<block_t>> *>(user);
+        levels[level].resize(bytes / sizeof(block_t));
+        return levels[level].data();
+    };
     // bc7enc_compress_block_params_init() defaults, as the reference uses them (:73-74); NULL selects them
     const uint32_t mode = compress_info.mode == BC7 ? VKT_BCN_MODE_BC7 : VKT_BCN_MODE_BC5;
-    const int rc = vkt_bcn_cuda_compress(context.ctx, mode, static_cast<const uint8_t *>(image->data()), image->width(), image->height(),
-                                         image->num_components(), compress_info.generate_mipmaps ? 1 : 0, nullptr, level_ptrs);
+    const int rc = vkt_bcn_cuda_compress_alloc(context.ctx, mode, static_cast<const uint8_t *>(image->data()), image->width(), image->height(),
+                                               image->num_components(), compress_info.generate_mipmaps ? 1 : 0, nullptr, +alloc_level, &ret.levels);
     if(rc != VKT_BCN_OK)
     {
         throw std::runtime_error(std::string("vierkant::bcn::compress (CUDA): ") + vkt_bcn_cuda_last_error(context.ctx));

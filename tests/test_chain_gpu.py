@@ -187,3 +187,28 @@ def test_compress_pinned_and_pageable_buffers_agree(ctx, w, h, mips):
         ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, src.data_ptr(), w, h, 4, int(mips), None, ptrs))
         for l in range(plan.num_levels):
             assert np.array_equal(outs[l].numpy(), want[l]), (pin_in, pin_out, l)
+
+
+def test_compress_alloc_matches_compress_and_reports_allocator_failure(ctx):
+    """vkt_bcn_cuda_compress_alloc (destinations asked for while the GPU works -- what the C++ drop-in uses for its
+    std::vector levels) == vkt_bcn_cuda_compress; an allocator that returns null fails the call cleanly."""
+    import ctypes as C
+    for (w, h, kind, mode) in [(1024, 512, 1, capi.MODE_BC7), (123, 81, 1, capi.MODE_BC7), (2048, 2048, 0, capi.MODE_BC7), (256, 256, 0, capi.MODE_BC5)]:
+        img = synth.make_texture(w, h, kind, seed=w + h)
+        _, want = ctx.compress(img, mode, True)
+        got = ctx.compress_alloc(img, mode, True)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    img = synth.make_texture(256, 256, 0)
+    calls = []
+
+    def failing(_user, level, nbytes):
+        calls.append(level)
+        return None if level == 1 else np.zeros(nbytes, dtype=np.uint8).ctypes.data  # (the array dies: never written because the call aborts)
+
+    cb = capi.ALLOC_FN(failing)
+    rc = ctx.lib.vkt_bcn_cuda_compress_alloc(ctx.handle, capi.MODE_BC7, img.ctypes.data, 256, 256, 4, 1, None, cb, None)
+    assert rc == capi.ERR_OOM and calls == [0, 1]
+    _, again = ctx.compress(img, capi.MODE_BC7, True)  # the context is still usable
+    assert np.array_equal(again[0], ctx.encode_bc7(ctx.resize_u8(img, 256, 256)))

@@ -16,6 +16,7 @@ from vierkant_b200 import capi, synth  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=4096)
 ap.add_argument("--kind", type=int, default=0)
+ap.add_argument("--pageable", action="store_true", help="plain (unpinned) host buffers on both sides, as the C++ drop-in passes them")
 a = ap.parse_args()
 
 # link rates: pinned host <-> device, 256 MB
@@ -32,9 +33,11 @@ for name, fn in (("H2D", lambda: d.copy_(h, non_blocking=True)), ("D2H", lambda:
     torch.cuda.synchronize()
     print(f"{name}: {4 * (256 << 20) / (e0.elapsed_time(e1) * 1e-3) * 1e-9:.1f} GB/s", file=sys.stderr)
 
-img = torch.from_numpy(synth.make_texture(a.size, a.size, a.kind)).pin_memory()
+img = torch.from_numpy(synth.make_texture(a.size, a.size, a.kind))
+img = img if a.pageable else img.pin_memory()
 plan = capi.compress_plan(a.size, a.size, True)
-outs = [torch.empty((int(plan.level_num_blocks[l]), 16), dtype=torch.uint8).pin_memory() for l in range(plan.num_levels)]
+outs = [torch.zeros((int(plan.level_num_blocks[l]), 16), dtype=torch.uint8) for l in range(plan.num_levels)]
+outs = outs if a.pageable else [o.pin_memory() for o in outs]
 ptrs = (C.c_void_p * plan.num_levels)(*[t.data_ptr() for t in outs])
 p = capi.default_params()
 with capi.BcnContext([0]) as ctx:

@@ -71,7 +71,9 @@ EXPORTS = [
     "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device", "vkt_bcn_cuda_compress_batch",
     "vkt_bcn_cuda_compress_shard_plan", "vkt_bcn_cuda_compress_shard_rows", "vkt_bcn_cuda_compress_shard_begin",
     "vkt_bcn_cuda_compress_shard_end", "vkt_bcn_cuda_host_register", "vkt_bcn_cuda_host_unregister",
+    "vkt_bcn_cuda_compress_alloc",
 ]
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t)  # vkt_bcn_alloc_fn
 
 _lib = None
 
@@ -106,6 +108,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.vkt_bcn_cuda_compress_plan.argtypes = [u32, u32, C.c_int, C.POINTER(Plan)]
     L.vkt_bcn_cuda_compress.argtypes = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), C.POINTER(vp)]
     L.vkt_bcn_cuda_compress_batch.argtypes = [vp, C.POINTER(Source), u32, C.c_int, C.POINTER(Bc7Params)]
+    L.vkt_bcn_cuda_compress_alloc.argtypes = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), ALLOC_FN, vp]
     L.vkt_bcn_cuda_compress_shard_plan.argtypes = [u32, u32, C.c_int, u32, C.POINTER(ShardPlan)]
     L.vkt_bcn_cuda_compress_shard_rows.argtypes = [u32, u32, C.c_int, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
     shard_args = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), u32, u32, C.POINTER(vp), vp]
@@ -278,6 +281,22 @@ class BcnContext:
         pp = C.byref(params) if params is not None else None
         self._check(self.lib.vkt_bcn_cuda_compress(self.handle, mode, _ptr(img), w, h, c, int(generate_mipmaps), pp, ptrs))
         return plan, levels
+
+    def compress_alloc(self, img: np.ndarray, mode: int = MODE_BC7, generate_mipmaps: bool = False,
+                       params: Bc7Params | None = None) -> list[np.ndarray]:
+        """vkt_bcn_cuda_compress_alloc: the level arrays are allocated by a callback while the GPU already works."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w, c = img.shape
+        levels = {}
+
+        def alloc(_user, level, nbytes):
+            levels[level] = np.zeros((nbytes // 16, 16), dtype=np.uint8)
+            return levels[level].ctypes.data
+
+        cb = ALLOC_FN(alloc)
+        pp = C.byref(params) if params is not None else None
+        self._check(self.lib.vkt_bcn_cuda_compress_alloc(self.handle, mode, _ptr(img), w, h, c, int(generate_mipmaps), pp, cb, None))
+        return [levels[l] for l in sorted(levels)]
 
     def compress_shard_begin(self, mode: int, pixels, width: int, height: int, comps: int, generate_mipmaps: bool,
                              params: Bc7Params | None, rank: int, world: int, level_ptrs, handover) -> None:

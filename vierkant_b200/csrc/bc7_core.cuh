@@ -512,7 +512,8 @@ VKT_FN uint64_t solid_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<ST
 
 // ---------------------------------------------------------------------------------------------------- evaluate_solution
 // bc7enc.cpp:645-831.  lo/hi are quantised endpoints (no p-bits), pbits bit0/bit1.  Updates `best` on strict improvement.
-template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE>
+// ROOMY: the calling kernel runs at two CTAs per SM (alpha blocks, uber levels) and has registers to spare.
+template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE, bool ROOMY = false>
 VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uint32_t lo, uint32_t hi, uint32_t pbits, Cell &best)
 {
     typedef ModeTraits<MODE> M;
@@ -573,6 +574,47 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
         {
             // error < 2^28 for every texel (checked on the host from the weights): key = err * 16 + j, one min per candidate.
             const uint32_t w0 = P.w16[0], w1 = P.w16[1], w2 = P.w16[2], w3 = P.w16[3];
+#if defined(VKT_EVAL_PAIR)
+            // two texels per trip (independent key chains) where the register budget allows it: the kernels that run at two
+            // CTAs per SM (alpha blocks, uber levels) have few warps to hide the dependent-issue latency of one chain
+            constexpr bool PAIR = ROOMY && (N <= VKT_EVAL_PAIR);
+#else
+            constexpr bool PAIR = false;
+#endif
+            if(PAIR)
+            {
+                for(int k = 0; k < cell.n; k += 2)
+                {
+                    const bool two = (k + 1 < cell.n);
+                    const Texel t0 = L.at(cell.at(k)), t1 = L.at(cell.at(two ? k + 1 : k));
+                    const int l20 = t0.l, ncr20 = -t0.cr, ncb20 = -t0.cb, l21 = t1.l, ncr21 = -t1.cr, ncb21 = -t1.cb;
+                    const int a20 = ALPHA ? (int) (t0.px >> 24) : 0, a21 = ALPHA ? (int) (t1.px >> 24) : 0;
+                    uint32_t key0 = 0xFFFFFFFFu, key1 = 0xFFFFFFFFu;
+#pragma unroll
+                    for(int j = 0; j < N; ++j)
+                    {
+                        const int dl0 = (pl[j] - l20) >> 8, dcr0 = sub_alu(pcr[j], ncr20) >> 8, dcb0 = sub_alu(pcb[j], ncb20) >> 8;
+                        const int dl1 = (pl[j] - l21) >> 8, dcr1 = sub_alu(pcr[j], ncr21) >> 8, dcb1 = sub_alu(pcb[j], ncb21) >> 8;
+                        uint32_t e0 = w0 * (uint32_t) (dl0 * dl0) + (uint32_t) j, e1 = w0 * (uint32_t) (dl1 * dl1) + (uint32_t) j;
+                        e0 += w1 * (uint32_t) (dcr0 * dcr0), e1 += w1 * (uint32_t) (dcr1 * dcr1);
+                        e0 += w2 * (uint32_t) (dcb0 * dcb0), e1 += w2 * (uint32_t) (dcb1 * dcb1);
+                        if(ALPHA)
+                        {
+                            const int da0 = pa[j] - a20, da1 = pa[j] - a21;
+                            e0 += w3 * (uint32_t) (da0 * da0), e1 += w3 * (uint32_t) (da1 * da1);
+                        }
+                        key0 = umin(key0, e0), key1 = umin(key1, e1);
+                    }
+                    total += (uint64_t) (key0 >> 4);
+                    sel |= (uint64_t) (key0 & 15u) << (4 * k);
+                    if(two)
+                    {
+                        total += (uint64_t) (key1 >> 4);
+                        sel |= (uint64_t) (key1 & 15u) << (4 * (k + 1));
+                    }
+                }
+            }
+            else
             for(int k = 0; k < cell.n; ++k)
             {
                 const int i = cell.at(k);
@@ -675,7 +717,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
 
 // ---------------------------------------------------------------------------------------------------- find_optimal_solution
 // bc7enc.cpp:868-1099 (+ fixDegenerateEndpoints :833-866).  xl/xh are float endpoints in [0,1] (saturated here).
-template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE>
+template<int MODE, bool ALPHA, bool PERC, int KV, int STRIDE, bool ROOMY = false>
 VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, const float xl_in[4], const float xh_in[4],
                     Cell &best)
 {
@@ -849,7 +891,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi) || ((bpb & 3u) != (best.pbits & 3u)))
         {
-            evaluate<MODE, ALPHA, PERC, KV, STRIDE>(P, L, cell, blo, bhi, bpb, best);
+            evaluate<MODE, ALPHA, PERC, KV, STRIDE, ROOMY>(P, L, cell, blo, bhi, bpb, best);
         }
     }
     else
@@ -867,7 +909,7 @@ VKT_FN uint64_t fit(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L
         }
         if((best.err == kNoErr) || (blo != best.lo) || (bhi != best.hi))
         {
-            evaluate<MODE, ALPHA, PERC, KV, STRIDE>(P, L, cell, blo, bhi, best.pbits, best);
+            evaluate<MODE, ALPHA, PERC, KV, STRIDE, ROOMY>(P, L, cell, blo, bhi, best.pbits, best);
         }
     }
     return best.err;
@@ -1149,7 +1191,7 @@ VKT_FN uint64_t compress_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             }
             least_squares<MODE, ALPHA, STRIDE>(T, L, cell, trial, xl, xh);
         }
-        if(!fit<MODE, ALPHA, PERC, KV, STRIDE>(T, P, L, cell, xl, xh, out)) { return 0; }
+        if(!fit<MODE, ALPHA, PERC, KV, STRIDE, (UBER || ALPHA || MODE == 5)>(T, P, L, cell, xl, xh, out)) { return 0; }
 
         // advance
         if(stage == 0)
@@ -1286,12 +1328,27 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
         };
         if(UNI)
         {
+#if defined(VKT_EST_BBOX_PREFETCH)
+            // software-pipelined: the next pair's texels are requested before the current pair is folded in, so the shared
+            // load latency hides behind the min / max work (the last trip re-requests its own pair: no branch, no overrun)
+            EstPair w = trips[q0];
+            uint32_t v0 = L.px((int) w.i0), v1 = L.px((int) w.i1);
+#pragma unroll 1
+            for(uint32_t q = q0; q < q1; ++q)
+            {
+                w = trips[umin(q + 1u, q1 - 1u)];
+                const uint32_t n0v = L.px((int) w.i0), n1v = L.px((int) w.i1);
+                grow(v0, v1);
+                v0 = n0v, v1 = n1v;
+            }
+#else
 #pragma unroll 1
             for(uint32_t q = q0; q < q1; ++q)
             {
                 const EstPair w = trips[q];
                 grow(L.px((int) w.i0), L.px((int) w.i1));
             }
+#endif
         }
         else
         {

@@ -219,11 +219,11 @@ static cudaError_t bc7_kernel_attributes()
 {
     cudaError_t e = bc7_kernel_attribute<true, true, false, false>();
     if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true, false>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, false, true>(); }
+    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true, true>(); }
 #ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false, false>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, true, false>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, false, true>(); }
-    if(e == cudaSuccess) { e = bc7_kernel_attribute<true, true, true, true>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, false, true>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<true, false, true, true>(); }
     if(e == cudaSuccess) { e = bc7_kernel_attribute<false, true, false, true>(); }
@@ -294,6 +294,8 @@ struct DeviceSlot
         const void *src;
         void *dst;
         size_t bytes;
+        uint32_t level = 0;// of a compress() chain (a deferred destination is resolved from level + offset)
+        size_t offset = 0;
     };
     std::vector<PendingCopy> pending;
     bool src_in_place = false;// the running chain reads its source where the caller keeps it (device memory of this device)
@@ -491,11 +493,11 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
 #endif
                 case 15: go(bc7_encode_kernel<true, true, true, false, kBc7ThreadsAlpha>); break;
                 case 14: go(bc7_encode_kernel<true, true, false, false, kBc7Threads>); break;
-#ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY// (tuning builds compile the two default-parameter kernels only)
-                case 11: go(bc7_encode_kernel<false, true, true, false, kBc7ThreadsAlpha>); break;
-                case 10: go(bc7_encode_kernel<false, true, false, false, kBc7Threads>); break;
                 case 7: go(bc7_encode_kernel<true, true, true, true, kBc7ThreadsAlpha>); break;
                 case 6: go(bc7_encode_kernel<true, true, false, true, kBc7Threads>); break;
+#ifndef VKT_BC7_DEV_DEFAULT_VARIANTS_ONLY// (tuning builds compile the perceptual 28-bit-key kernels only: defaults and uber levels)
+                case 11: go(bc7_encode_kernel<false, true, true, false, kBc7ThreadsAlpha>); break;
+                case 10: go(bc7_encode_kernel<false, true, false, false, kBc7Threads>); break;
                 case 5: go(bc7_encode_kernel<true, false, true, true, kBc7ThreadsAlpha>); break;
                 case 4: go(bc7_encode_kernel<true, false, false, true, kBc7Threads>); break;
                 case 3: go(bc7_encode_kernel<false, true, true, true, kBc7ThreadsAlpha>); break;
@@ -876,7 +878,7 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
                 }
                 cudaEvent_t landed = s->event_pool[s->events_used++];
                 VKT_CUDA(ctx, cudaEventRecord(landed, st));
-                s->pending.push_back({landed, staged, user, bytes});
+                s->pending.push_back({landed, staged, user, bytes, 0u, size_t(0)});
             }
             else { VKT_CUDA(ctx, cudaMemcpyAsync(user, static_cast<uint8_t *>(s->d_out) + p.out_off, bytes, cudaMemcpyDefault, st)); }
             count(ctx, 0, 0, bytes);
@@ -1064,6 +1066,13 @@ int vkt_bcn_cuda_compress(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
 {
     if(!ctx) { return VKT_BCN_ERR_INVALID; }
     return compress_chain(ctx, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks);
+}
+
+int vkt_bcn_cuda_compress_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                                int generate_mipmaps, const vkt_bc7_params *params, vkt_bcn_alloc_fn alloc_level, void *user)
+{
+    if(!ctx) { return VKT_BCN_ERR_INVALID; }
+    return compress_chain_alloc(ctx, mode, pixels, width, height, comps, generate_mipmaps, params, alloc_level, user);
 }
 
 // ---- one chain split over several processes (one GPU each) ------------------------------------------------------------

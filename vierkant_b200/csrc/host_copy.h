@@ -8,14 +8,49 @@
 // caller's memory and those with several threads while the GPU works on the bands already queued.
 #pragma once
 #include <condition_variable>
+#include <cstdint>
 #include <cstring>
 #include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace vkt
 {
+
+// memcpy whose stores bypass the cache (MOVNTDQ): the destinations here are read next by a DMA engine (pinned staging) or
+// much later by the caller (its block vectors), never by this core, so write-allocating their lines only adds a third
+// stream of memory traffic to a copy that is bandwidth-bound (measured on the B200 box's host: 19 -> 2x GB/s with 8 threads).
+static inline void stream_copy(void *dst, const void *src, size_t bytes)
+{
+#if defined(__SSE2__)
+    char *d = static_cast<char *>(dst);
+    const char *s = static_cast<const char *>(src);
+    if(bytes < 4096)
+    {
+        std::memcpy(d, s, bytes);
+        return;
+    }
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    std::memcpy(d, s, head);
+    d += head, s += head, bytes -= head;
+    size_t n64 = bytes / 64;
+    for(; n64; --n64, d += 64, s += 64)
+    {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d), a), _mm_stream_si128(reinterpret_cast<__m128i *>(d + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 32), c), _mm_stream_si128(reinterpret_cast<__m128i *>(d + 48), e);
+    }
+    _mm_sfence();
+    std::memcpy(d, s, bytes & 63);
+#else
+    std::memcpy(dst, src, bytes);
+#endif
+}
 
 class CopyPool
 {
@@ -43,7 +78,7 @@ public:
         const size_t parts = std::min<size_t>(threads_.size() + 1, bytes / kMinChunk);
         if(parts <= 1)
         {
-            std::memcpy(dst, src, bytes);
+            stream_copy(dst, src, bytes);
             return;
         }
         std::lock_guard<std::mutex> one_call(call_);// one parallel copy at a time (callers of different slots may meet here)
@@ -59,7 +94,7 @@ public:
             }
         }
         work_.notify_all();
-        std::memcpy(dst, src, mine);
+        stream_copy(dst, src, mine);
         std::unique_lock<std::mutex> g(m_);
         done_.wait(g, [this] { return outstanding_ == 0; });
     }
@@ -85,7 +120,7 @@ private:
             const Job j = jobs_.front();
             jobs_.pop_front();
             g.unlock();
-            std::memcpy(j.dst, j.src, j.bytes);
+            stream_copy(j.dst, j.src, j.bytes);
             g.lock();
             if(--outstanding_ == 0) { done_.notify_all(); }
         }

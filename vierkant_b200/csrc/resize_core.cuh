@@ -302,16 +302,19 @@ struct ChainShard
     cudaEvent_t handed_over = nullptr;// out (phase 1, rank > 0): fires when this worker's rows have landed in `handover`
 };
 
+// level_blocks == nullptr (vkt_bcn_cuda_compress_alloc): the destinations are not known yet.  Every level is then staged in the
+// slot's pinned mirror and the pending hand-overs carry (level, offset); the caller fills in the addresses before chain_wait().
 static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots, uint32_t mode, const uint8_t *pixels, uint32_t width,
                          uint32_t height, uint32_t comps, int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks,
                          std::vector<std::pair<cudaEvent_t, std::string>> *marks_out, ChainShard *shard = nullptr)
 {
+    const bool deferred = (level_blocks == nullptr) && !shard;
     if(mode != VKT_BCN_MODE_BC7 && mode != VKT_BCN_MODE_BC5) { return fail(ctx, VKT_BCN_ERR_INVALID, "unknown mode %u", mode); }
-    if(!pixels || !level_blocks || !width || !height) { return fail(ctx, VKT_BCN_ERR_INVALID, "null buffer or empty image"); }
+    if(!pixels || (!level_blocks && !deferred) || !width || !height) { return fail(ctx, VKT_BCN_ERR_INVALID, "null buffer or empty image"); }
     if(comps != 3 && comps != 4) { return fail(ctx, VKT_BCN_ERR_INVALID, "comps must be 3 or 4 (got %u)", comps); }
     vkt_bcn_plan plan;
     if(vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps, &plan)) { return fail(ctx, VKT_BCN_ERR_INVALID, "bad size"); }
-    for(uint32_t l = 0; l < plan.num_levels; ++l)
+    for(uint32_t l = 0; l < plan.num_levels && !deferred; ++l)
     {
         if(!level_blocks[l]) { return fail(ctx, VKT_BCN_ERR_INVALID, "level_blocks[%u] is null", l); }
     }
@@ -330,7 +333,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     // pinned buffers of the slot with the copy pool (host_copy.h); pinned and device memory is used in place.
     const bool stage_in = is_pageable_host(pixels);
     bool stage_out[16] = {}, any_stage_out = false;
-    for(uint32_t l = 0; l < plan.num_levels; ++l) { stage_out[l] = is_pageable_host(level_blocks[l]), any_stage_out = any_stage_out || stage_out[l]; }
+    for(uint32_t l = 0; l < plan.num_levels; ++l) { stage_out[l] = deferred || is_pageable_host(level_blocks[l]), any_stage_out = any_stage_out || stage_out[l]; }
     size_t lvl_off[16], lvl_total = 0, out_off[16], out_total = 0;
     for(uint32_t l = 0; l < plan.num_levels; ++l)
     {
@@ -430,7 +433,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
     }
     // blocks at d_ptr (inside slot sl's d_out) -> bytes [off, off + bytes) of the caller's level l, queued on st
     auto fetch = [&](DeviceSlot *sl, uint32_t l, size_t off, const void *d_ptr, size_t bytes, cudaStream_t st) -> int {
-        uint8_t *user = static_cast<uint8_t *>(level_blocks[l]) + off;
+        uint8_t *user = deferred ? nullptr : static_cast<uint8_t *>(level_blocks[l]) + off;
         if(stage_out[l])
         {
             uint8_t *staged = static_cast<uint8_t *>(sl->h_out) + (static_cast<const uint8_t *>(d_ptr) - static_cast<const uint8_t *>(sl->d_out));
@@ -438,7 +441,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
             cudaEvent_t landed;
             VKT_CUDA(ctx, new_event(&landed));
             VKT_CUDA(ctx, cudaEventRecord(landed, st));
-            sl->pending.push_back({landed, staged, user, bytes});// chain_wait() moves it on once the event has fired
+            sl->pending.push_back({landed, staged, user, bytes, l, off});// chain_wait() moves it on once the event has fired
         }
         else { VKT_CUDA(ctx, cudaMemcpyAsync(user, d_ptr, bytes, cudaMemcpyDefault, st)); }
         count(ctx, 0, 0, bytes);
@@ -735,7 +738,7 @@ static int chain_wait(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots)
         for(const DeviceSlot::PendingCopy &pc: s->pending)
         {
             const cudaError_t e1 = cudaEventSynchronize(pc.ready);
-            if(e1 == cudaSuccess) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
+            if(e1 == cudaSuccess && pc.dst) { copy_pool(ctx).copy(pc.dst, pc.src, pc.bytes); }
             else if(e == cudaSuccess) { e = e1; }
         }
         s->pending.clear();
@@ -777,6 +780,43 @@ static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels
         }
     }
     return rc;
+}
+
+// vkt_bcn_cuda_compress_alloc: the chain is queued first; the caller's allocator is asked for every level's memory while the GPU
+// works (vierkant's compress_result_t::levels[l].resize() -- 22 MB of freshly mapped, zero-filled pages for a 4096^2 chain --
+// otherwise sits in front of the first upload), then the pieces are handed over as their downloads land.
+static int compress_chain_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
+                                int generate_mipmaps, const vkt_bc7_params *params, vkt_bcn_alloc_fn alloc_level, void *user)
+{
+    if(!alloc_level) { return fail(ctx, VKT_BCN_ERR_INVALID, "null allocator"); }
+    vkt_bcn_plan plan;
+    if(vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps, &plan)) { return fail(ctx, VKT_BCN_ERR_INVALID, "bad size"); }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    // The allocator runs on a helper thread while this one queues the chain (with a pageable source the queueing itself is
+    // host work: the source rows are staged band by band): level 0 first, one call at a time.
+    uint8_t *base[16] = {};
+    uint32_t failed_level = ~0u;
+    std::thread allocator([&] {
+        for(uint32_t l = 0; l < plan.num_levels; ++l)
+        {
+            base[l] = static_cast<uint8_t *>(alloc_level(user, l, size_t(plan.level_num_blocks[l]) * 16));
+            if(!base[l])
+            {
+                failed_level = l;
+                return;
+            }
+        }
+    });
+    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, nullptr, nullptr);
+    allocator.join();
+    if(!rc && failed_level != ~0u) { rc = fail(ctx, VKT_BCN_ERR_OOM, "the caller's allocator returned null for level %u", failed_level); }
+    for(DeviceSlot *s: ctx->slots)
+    {
+        for(DeviceSlot::PendingCopy &pc: s->pending) { pc.dst = (!rc && base[pc.level]) ? base[pc.level] + pc.offset : nullptr; }
+    }
+    const int rw = chain_wait(ctx, ctx->slots);
+    return rc ? rc : rw;
 }
 
 // Several textures (vkt_bcn_cuda_compress_batch): two lanes per device -- the primary slot and a second one with its own
