@@ -349,6 +349,7 @@ struct CtaScratch
     uint16_t info[STRIDE]; // best partition | running << 8
     uint16_t perm[STRIDE]; // slot -> thread whose block the slot's thread adopts
     uint32_t cnt[8][16];   // blocks per (thread index mod 8, key bin); zeroed by the kernel before its first barrier
+    uint32_t cnt2[8][8];   // blocks per (thread index mod 8, subset-size class): the second regrouping (encode_block); zeroed likewise
 };
 
 // A colour cell = n texels of the block, listed by the nibbles of `perm` (texel index of cell element k at bits [4k,4k+4)).
@@ -1847,8 +1848,10 @@ VKT_FN bool block_has_alpha(const Bc7KernelParams &P, const uint32_t px[16])
 // ALPHA == true is handle_alpha_block (:2139-2291).  The caller classifies blocks first so that a warp only ever holds
 // blocks of one kind; the whole warp must call this converged (estimate_partition is warp-cooperative).
 // L: the lane column with texels [0,16) filled; the YCbCr part is filled here.
+// gid: an identifier of the lane's block that the caller can map back to its output slot.  Returns the identifier of the
+// block this lane actually encoded -- on the device the CTA's opaque blocks change hands once (see below).
 template<bool PERC, int KV, bool ALPHA, bool UBER, int STRIDE>
-VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4])
+VKT_FN uint32_t encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t out[4], uint32_t gid = 0)
 {
     if(PERC) { prepare_lane<STRIDE>(L); }
     const CellRef whole = {kIdentityPerm, 16};
@@ -1867,6 +1870,35 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
     const bool do17 = ALPHA ? ((P.mode_mask & (1u << 7)) != 0) : ((P.max_partitions > 0) && (P.mode_mask & (1u << 1)));// warp-uniform
     uint32_t part17 = 0;
     if(!ALPHA && do17) { part17 = estimate_partition<false, PERC, KV, STRIDE>(T, P, L, true); }
+#if defined(__CUDA_ARCH__) && !defined(VKT_NO_SIZE_REGROUP)
+    // Second regrouping, by subset size.  The colour-cell searches of mode 1 loop over the texels of a subset, and the lanes
+    // of a warp hold partitions with different subset sizes: a raster-order warp runs max(8..15) + max(1..8) = 22 trips where
+    // one block needs 16 (20.4 of 32 lanes active in those loops).  Now that every block has its partition, the CTA's blocks
+    // are sorted by the size of their larger subset (8 classes) with the same counting sort as in estimate_partition -- within
+    // each class of thread index mod 8, so the adopted columns stay conflict-free -- and every lane KEEPS the block it
+    // adopts to the end of the kernel: what travels is the column pointer, the partition and the block's identifier (the
+    // caller stores the result in that block's slot).  Which lane encodes a block has no influence on the block's result.
+    if(!ALPHA && do17 && (STRIDE >= 64) && (STRIDE % 32 == 0))// CTA-uniform
+    {
+        CtaScratch<STRIDE> *S = reinterpret_cast<CtaScratch<STRIDE> *>(L.p - threadIdx.x + 16 * STRIDE);
+        const uint32_t n0 = T.est_n0[part17];
+        const uint32_t bin = umax(n0, 16u - n0) - 8u;// 0..7
+        const uint32_t cls = threadIdx.x & 7u;
+        const uint32_t pos = atomicAdd(&S->cnt2[cls][bin], 1u);
+        S->err[threadIdx.x] = gid;
+        S->info[threadIdx.x] = (uint16_t) part17;
+        __syncthreads();
+        uint32_t q = pos;
+#pragma unroll
+        for(uint32_t b = 0; b < 7; ++b) { q += (b < bin) ? S->cnt2[cls][b] : 0u; }
+        S->perm[(q / 4u) * 32u + (q % 4u) * 8u + cls] = (uint16_t) threadIdx.x;
+        __syncthreads();
+        const uint32_t src = S->perm[threadIdx.x];
+        gid = S->err[src];
+        part17 = S->info[src];
+        L.p = L.p + ((int) src - (int) threadIdx.x);
+    }
+#endif
 
     if(P.mode_mask & (1u << 6))
     {
@@ -1916,6 +1948,7 @@ VKT_FN void encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRI
         }
     }
     pack_block(T, sol, out);
+    return gid;
 }
 
 }// namespace vkt

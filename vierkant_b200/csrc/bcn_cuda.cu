@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : (UBER ? kBc7C
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tables);
         uint4 *dst = reinterpret_cast<uint4 *>(&s_tables);
         for(uint32_t i = threadIdx.x; i < kTab / 16; i += NT) { dst[i] = __ldg(src + i); }
-        if(threadIdx.x < 128) { (&s_scratch->cnt[0][0])[threadIdx.x] = 0u; }
+        if(threadIdx.x < 192) { (&s_scratch->cnt[0][0])[threadIdx.x] = 0u; }// cnt[8][16] and cnt2[8][8] are adjacent
     }
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
     const uint32_t ii = min(i, n - 1);// out-of-range lanes redo the last block (keeps warps converged), no store
@@ -199,8 +199,14 @@ __global__ void __launch_bounds__(NT, ALPHA ? kBc7CtasPerSmAlpha : (UBER ? kBc7C
     load_block_texels<NT>(I.img, I.comps, I.stride, I.vec16 != 0, b % I.blocks_x, b / I.blocks_x, lane.p);
     __syncthreads();
     uint32_t blk[4];
-    encode_block<PERC, KV, ALPHA, UBER, NT>(s_tables, P, lane, blk);
-    if(i < n) { I.out[b] = make_uint4(blk[0], blk[1], blk[2], blk[3]); }
+    // the lane may finish another block of the CTA than the one it loaded (encode_block regroups them): the block's index in
+    // the launch travels with it
+    const uint32_t done = encode_block<PERC, KV, ALPHA, UBER, NT>(s_tables, P, lane, blk, (i < n) ? g : 0xFFFFFFFFu);
+    if(done != 0xFFFFFFFFu)
+    {
+        const Bc7Image &J = B.im[batch_find(B, done)];
+        J.out[done - J.first_block] = make_uint4(blk[0], blk[1], blk[2], blk[3]);
+    }
 }
 
 constexpr size_t bc7_smem_bytes(bool alpha)
