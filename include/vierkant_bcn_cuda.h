@@ -223,6 +223,16 @@ int vkt_bcn_cuda_compress_shard_end(vkt_bcn_ctx *ctx, uint32_t mode, const uint8
 int vkt_bcn_cuda_host_register(vkt_bcn_ctx *ctx, void *ptr, size_t bytes);
 int vkt_bcn_cuda_host_unregister(vkt_bcn_ctx *ctx, void *ptr);
 
+/* The Vulkan hand-off: vierkant copies every level from the compress_result_t into a host-visible staging
+ * VkBuffer and uploads from there (create_compressed_texture, src/model/model_loading.cpp:460-494).  With the staging buffer's
+ * memory exported as an opaque fd (VK_KHR_external_memory_fd, vkGetMemoryFdKHR) this call maps it into the context's device
+ * `slot` (cudaImportExternalMemory + cudaExternalMemoryGetMappedBuffer); *d_ptr can then be passed as a level_blocks[l]
+ * destination (plus an offset) to vkt_bcn_cuda_compress / _batch / _shard_*, and the blocks land in the Vulkan buffer without
+ * touching the host.  CUDA takes ownership of `fd` on success.  Release with vkt_bcn_cuda_release_external before the Vulkan
+ * memory is freed.  INTEGRATION.md section 5 shows both sides. */
+int vkt_bcn_cuda_import_external_fd(vkt_bcn_ctx *ctx, int slot, int fd, uint64_t bytes, void **d_ptr, void **external_handle);
+int vkt_bcn_cuda_release_external(vkt_bcn_ctx *ctx, int slot, void *d_ptr, void *external_handle);
+
 /* Counters for the measurement harness: kernels launched / bytes copied by this context since creation. */
 typedef struct vkt_bcn_stats
 {

@@ -71,7 +71,7 @@ EXPORTS = [
     "vkt_bcn_cuda_measure_issue_peak", "vkt_bcn_cuda_encode_batch_device", "vkt_bcn_cuda_compress_batch",
     "vkt_bcn_cuda_compress_shard_plan", "vkt_bcn_cuda_compress_shard_rows", "vkt_bcn_cuda_compress_shard_begin",
     "vkt_bcn_cuda_compress_shard_end", "vkt_bcn_cuda_host_register", "vkt_bcn_cuda_host_unregister",
-    "vkt_bcn_cuda_compress_alloc",
+    "vkt_bcn_cuda_compress_alloc", "vkt_bcn_cuda_import_external_fd", "vkt_bcn_cuda_release_external",
 ]
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t)  # vkt_bcn_alloc_fn
 
@@ -114,6 +114,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     shard_args = [vp, u32, vp, u32, u32, u32, C.c_int, C.POINTER(Bc7Params), u32, u32, C.POINTER(vp), vp]
     L.vkt_bcn_cuda_compress_shard_begin.argtypes = shard_args
     L.vkt_bcn_cuda_compress_shard_end.argtypes = shard_args
+    L.vkt_bcn_cuda_import_external_fd.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.vkt_bcn_cuda_release_external.argtypes = [vp, C.c_int, vp, vp]
     L.vkt_bcn_cuda_host_register.argtypes = [vp, vp, C.c_size_t]
     L.vkt_bcn_cuda_host_unregister.argtypes = [vp, vp]
     L.vkt_bcn_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -311,6 +313,16 @@ class BcnContext:
         pp = C.byref(params) if params is not None else None
         self._check(self.lib.vkt_bcn_cuda_compress_shard_end(self.handle, mode, _ptr(pixels), width, height, comps, int(generate_mipmaps),
                                                              pp, rank, world, level_ptrs, None if handover is None else _ptr(handover)))
+
+    def import_external_fd(self, fd: int, nbytes: int, slot: int = 0) -> tuple[int, int]:
+        """Map external memory exported as an opaque fd (a Vulkan staging buffer, VK_KHR_external_memory_fd) into device `slot`.
+        Returns (device pointer, handle); CUDA owns the fd afterwards.  Release with release_external()."""
+        d_ptr, handle = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.vkt_bcn_cuda_import_external_fd(self.handle, slot, fd, nbytes, C.byref(d_ptr), C.byref(handle)))
+        return int(d_ptr.value), int(handle.value)
+
+    def release_external(self, d_ptr: int, handle: int, slot: int = 0) -> None:
+        self._check(self.lib.vkt_bcn_cuda_release_external(self.handle, slot, d_ptr, handle))
 
     def host_register(self, buf) -> None:
         """cudaHostRegister (portable) of a numpy array / torch tensor the caller keeps alive."""

@@ -1156,6 +1156,41 @@ int vkt_bcn_cuda_compress_shard_end(vkt_bcn_ctx *ctx, uint32_t mode, const uint8
     return rc;
 }
 
+int vkt_bcn_cuda_import_external_fd(vkt_bcn_ctx *ctx, int slot, int fd, uint64_t bytes, void **d_ptr, void **external_handle)
+{
+    if(!ctx || !d_ptr || !external_handle || fd < 0 || !bytes) { return ctx ? fail(ctx, VKT_BCN_ERR_INVALID, "bad external memory arguments") : VKT_BCN_ERR_INVALID; }
+    if(slot < 0 || slot >= int(ctx->slots.size())) { return fail(ctx, VKT_BCN_ERR_INVALID, "slot %d out of range", slot); }
+    *d_ptr = nullptr, *external_handle = nullptr;
+    VKT_CUDA(ctx, cudaSetDevice(ctx->slots[size_t(slot)]->device));
+    cudaExternalMemoryHandleDesc hd = {};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = bytes;
+    cudaExternalMemory_t ext = nullptr;
+    VKT_CUDA(ctx, cudaImportExternalMemory(&ext, &hd));
+    cudaExternalMemoryBufferDesc bd = {};
+    bd.offset = 0, bd.size = bytes;
+    void *p = nullptr;
+    const cudaError_t e = cudaExternalMemoryGetMappedBuffer(&p, ext, &bd);
+    if(e != cudaSuccess)
+    {
+        cudaDestroyExternalMemory(ext);
+        return fail(ctx, VKT_BCN_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer failed: %s", cudaGetErrorString(e));
+    }
+    *d_ptr = p, *external_handle = ext;
+    return VKT_BCN_OK;
+}
+
+int vkt_bcn_cuda_release_external(vkt_bcn_ctx *ctx, int slot, void *d_ptr, void *external_handle)
+{
+    if(!ctx || !external_handle) { return VKT_BCN_ERR_INVALID; }
+    if(slot < 0 || slot >= int(ctx->slots.size())) { return fail(ctx, VKT_BCN_ERR_INVALID, "slot %d out of range", slot); }
+    VKT_CUDA(ctx, cudaSetDevice(ctx->slots[size_t(slot)]->device));
+    if(d_ptr) { VKT_CUDA(ctx, cudaFree(d_ptr)); }// the mapping of cudaExternalMemoryGetMappedBuffer
+    VKT_CUDA(ctx, cudaDestroyExternalMemory(static_cast<cudaExternalMemory_t>(external_handle)));
+    return VKT_BCN_OK;
+}
+
 int vkt_bcn_cuda_host_register(vkt_bcn_ctx *ctx, void *ptr, size_t bytes)
 {
     if(!ctx || !ptr || !bytes) { return VKT_BCN_ERR_INVALID; }
