@@ -438,6 +438,25 @@ def main():
     b1 = ctx.stats()
     barrier()
 
+    # the same call with DEVICE destinations (the blocks land in device memory -- an imported Vulkan staging
+    # buffer -- and never cross to the host): only the source upload uses the link.  Informational; all ranks at once.
+    devdst_ms = None
+    if batch_srcs is None:
+        dd_ptrs = (C.c_void_p * len(dims))(*[t.data_ptr() for t in dev_out[0]])
+
+        def step_devdst(i):
+            ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, host_src[i % ROTATE].data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                     C.byref(params), dd_ptrs))
+        for i in range(args.warmup):
+            step_devdst(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_devdst(i)
+        torch.cuda.synchronize()
+        devdst_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        barrier()
+
     # the same call with PAGEABLE host buffers -- what the C++ drop-in passes (a malloc'ed crocore image in, std::vector blocks out):
     # informational, N = 1 / single-texture workloads only, outside every other timed region
     pageable_ms = None
@@ -488,10 +507,10 @@ def main():
         except Exception as e:  # noqa: BLE001
             dropin = {"value": None, "error": repr(e)}
 
-    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tms = torch.tensor([ms, e2e_s * 1e3, devdst_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(tms[0]), float(tms[1])
+    ms_max, e2e_ms_max, devdst_ms_max = float(tms[0]), float(tms[1]), float(tms[2])
 
     # ---- ONE chain sharded over the ranks (north_star: 16K-class strong scaling) ----------------------------------------
     strong = {}
@@ -539,6 +558,10 @@ def main():
             "e2e_pageable": (None if pageable_ms is None else
                              {"value": npix / (pageable_ms * 1e-3) * 1e-6, "unit": "Mpixel/s", "ms_per_step": pageable_ms,
                               "note": "same call, pageable host buffers as the C++ drop-in passes them (staged by the library); informational"}),
+            "e2e_device_destinations": (None if not devdst_ms_max else
+                                        {"value": npix * world / (devdst_ms_max * 1e-3) * 1e-6, "unit": "Mpixel/s", "ms_per_step": devdst_ms_max,
+                                         "note": "same call, pinned host source in, every level's blocks left in device memory (the N4 hand-off: an imported "
+                                                 "Vulkan staging buffer as destination); no D2H; informational"}),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "alu", "achieved": achieved * 1e-12, "peak": alu_peak * 1e-12, "unit": "Tlane-op/s",
