@@ -34,6 +34,9 @@ struct DeviceAxis
     int *d_start = nullptr;
     int2 *d_tap = nullptr;// {input sample, coefficient bits}: one 64-bit load per tap
     std::vector<int> first_in, last_in;// per output: smallest / largest input sample (band planning)
+    // Regular axes (every power-of-two chain level): output o reads exactly `reg_taps` samples, clamp(reg_step * o + reg_off + t),
+    // t ascending -- 3 taps at 1:1 (Mitchell, x-1 .. x+1), 8 taps at 2:1 (2x-3 .. 2x+4).  reg_taps == 0: irregular, general passes.
+    int reg_taps = 0, reg_step = 0, reg_off = 0;
     ~DeviceAxis()
     {
         cudaFree(d_start);
@@ -147,6 +150,85 @@ __global__ void __launch_bounds__(256) resize_v_kernel(const float *__restrict__
     }
 }
 
+// Fused pass for regular axes (DeviceAxis::reg_*) and RGBA: one thread owns an output column and walks a strip of output rows.
+// Its S * T horizontal taps (sample, coefficient) stay in registers for the whole strip; the horizontally filtered samples of
+// the last T - S input rows stay in a register window, so every input row is filtered once per strip and the vertical sum
+// reads registers.  The arithmetic is that of resize_h_kernel followed by resize_v_kernel, operation for operation (same
+// order, same coefficient bits, multiply and add rounded separately), so the bytes are the same -- but there is no fp32 band in
+// memory and an output sample costs S * T coalesced 32-bit loads instead of ~30 (1:1) to ~180 (2:1) L1 wavefronts per warp row.
+// Rows outside the image are clamped copies of the edge row, recomputed (the tap lists name them as separate terms).
+template<int S, int T>
+__global__ void __launch_bounds__(128) resize_fused_kernel(const uint8_t *__restrict__ src, int in_w, int in_h, int out_w, int y0, int y1, int strip,
+                                                            int off_y, const int *__restrict__ xstart, const int2 *__restrict__ xtap,
+                                                            const int *__restrict__ ystart, const int2 *__restrict__ ytap, uint8_t *__restrict__ dst)
+{
+    const int x = blockIdx.x * 128 + int(threadIdx.x);
+    const int ya = y0 + int(blockIdx.y) * strip, yb = min(ya + strip, y1);
+    if(x >= out_w || ya >= yb) { return; }
+    int hx[T];
+    float hc[T];
+    {
+        const int t0 = __ldg(xstart + x);
+#pragma unroll
+        for(int t = 0; t < T; ++t)
+        {
+            const int2 tp = __ldg(xtap + t0 + t);
+            hx[t] = tp.x, hc[t] = __int_as_float(tp.y);
+        }
+    }
+    // horizontally filtered sample of (virtual) input row v at this thread's column
+    auto hrow = [&](int v) -> float4 {
+        const int r = v < 0 ? 0 : (v >= in_h ? in_h - 1 : v);
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(src) + size_t(r) * size_t(in_w);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for(int t = 0; t < T; ++t)
+        {
+            const uint32_t q = __ldg(row + hx[t]);
+            a0 = __fadd_rn(a0, __fmul_rn(resize_decode_u8(q & 255u), hc[t]));
+            a1 = __fadd_rn(a1, __fmul_rn(resize_decode_u8((q >> 8) & 255u), hc[t]));
+            a2 = __fadd_rn(a2, __fmul_rn(resize_decode_u8((q >> 16) & 255u), hc[t]));
+            a3 = __fadd_rn(a3, __fmul_rn(resize_decode_u8(q >> 24), hc[t]));
+        }
+        return make_float4(a0, a1, a2, a3);
+    };
+    float4 win[T];// win[t] = filtered virtual row S * y + off_y + t of the current output row y
+#pragma unroll
+    for(int t = 0; t < T - S; ++t) { win[t + S] = hrow(S * ya + off_y + t); }
+    uint32_t *out = reinterpret_cast<uint32_t *>(dst) + size_t(ya) * size_t(out_w) + size_t(x);
+#pragma unroll 1
+    for(int y = ya; y < yb; ++y, out += out_w)
+    {
+#pragma unroll
+        for(int t = 0; t < T - S; ++t) { win[t] = win[t + S]; }
+#pragma unroll
+        for(int t = T - S; t < T; ++t) { win[t] = hrow(S * y + off_y + t); }
+        const int t0 = __ldg(ystart + y);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for(int t = 0; t < T; ++t)
+        {
+            const float w = __int_as_float(__ldg(ytap + t0 + t).y);
+            a0 = __fadd_rn(a0, __fmul_rn(win[t].x, w));
+            a1 = __fadd_rn(a1, __fmul_rn(win[t].y, w));
+            a2 = __fadd_rn(a2, __fmul_rn(win[t].z, w));
+            a3 = __fadd_rn(a3, __fmul_rn(win[t].w, w));
+        }
+        uint32_t q = 0;
+        const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for(int c = 0; c < 4; ++c)
+        {
+            float f = acc[c];
+            f = f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f);// stbir__saturate :572-581
+            const float sc = __fmul_rn(f, 255.0f);
+            const int i = __float2int_rz(sc);// (int)((double) s + 0.5), as in resize_v_kernel
+            q |= (uint32_t(i) + ((__fsub_rn(sc, (float) i) >= 0.5f) ? 1u : 0u)) << (8 * c);
+        }
+        *out = q;
+    }
+}
+
 }// namespace vkt
 
 // per-slot cache of axis tables (keyed by in/out size); lives beside the DeviceSlot, guarded by the slot mutex
@@ -204,6 +286,23 @@ static int get_axis(vkt_bcn_ctx *ctx, DeviceSlot *s, int in, int out, vkt_axis_p
         if(h.start[size_t(o)] == h.start[size_t(o) + 1]) { lo = hi = 0; }
         d->first_in[size_t(o)] = lo, d->last_in[size_t(o)] = hi;
     }
+    // regular structure?  (every output: the same number of taps, samples clamp(step * o + off + t))
+    if(out > 0 && (in == out || in == 2 * out))
+    {
+        const int step = in / out, T = h.start[1] - h.start[0];
+        bool regular = (T == 3 && step == 1) || (T == 8 && step == 2);
+        const int off = regular ? (step == 1 ? -1 : -3) : 0;
+        for(int o = 0; o < out && regular; ++o)
+        {
+            regular = (h.start[size_t(o) + 1] - h.start[size_t(o)] == T);
+            for(int t = 0; t < T && regular; ++t)
+            {
+                const int v = step * o + off + t;
+                regular = h.idx[size_t(h.start[size_t(o)] + t)] == (v < 0 ? 0 : (v >= in ? in - 1 : v));
+            }
+        }
+        if(regular) { d->reg_taps = T, d->reg_step = step, d->reg_off = off; }
+    }
     *res = d;
     m[{in, out}] = std::move(d);
     return VKT_BCN_OK;
@@ -221,6 +320,32 @@ static int resize_device(vkt_bcn_ctx *ctx, DeviceSlot *s, const uint8_t *d_src, 
     int rc = get_axis(ctx, s, int(w), int(ow), &ax);
     if(rc) { return rc; }
     if((rc = get_axis(ctx, s, int(h), int(oh), &ay))) { return rc; }
+    static const bool no_fused = getenv("VKT_BCN_NO_FUSED_RESIZE") != nullptr;// (tuning / A-B tests)
+    // (a thread of the fused pass walks a strip of rows in sequence: calls with few output samples -- the small levels of a
+    // chain -- would leave the device to a handful of long-running threads; they keep the sample-parallel general passes)
+    const uint64_t outputs = uint64_t(out_y1 > out_y0 ? out_y1 - out_y0 : 0) * ow;
+    if(comps == 4 && ax->reg_taps && ax->reg_taps == ay->reg_taps && ax->reg_step == ay->reg_step && !no_fused && outputs >= (1u << 20) &&
+       (reinterpret_cast<uintptr_t>(d_src) & 3u) == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 3u) == 0)
+    {
+        // regular axes (every level of a power-of-two chain): the fused pass, no fp32 band
+        const uint32_t rows = out_y1 - out_y0;
+        static const int strip_env = getenv("VKT_BCN_RESIZE_STRIP") ? atoi(getenv("VKT_BCN_RESIZE_STRIP")) : 0;// (tuning)
+        const int strip = strip_env > 0 ? strip_env : 16;// measured on 4096^2 chains: 8 / 16 / 32 rows per strip 3.10 / 3.08 / 3.15 ms (general passes: 3.23)
+        const dim3 grid((ow + 127u) / 128u, (rows + uint32_t(strip) - 1u) / uint32_t(strip));
+        if(ax->reg_step == 1)
+        {
+            resize_fused_kernel<1, 3><<<grid, 128, 0, stream>>>(d_src, int(w), int(h), int(ow), int(out_y0), int(out_y1), strip, ay->reg_off, ax->d_start,
+                                                                 ax->d_tap, ay->d_start, ay->d_tap, d_dst);
+        }
+        else
+        {
+            resize_fused_kernel<2, 8><<<grid, 128, 0, stream>>>(d_src, int(w), int(h), int(ow), int(out_y0), int(out_y1), strip, ay->reg_off, ax->d_start,
+                                                                 ax->d_tap, ay->d_start, ay->d_tap, d_dst);
+        }
+        VKT_CUDA(ctx, cudaGetLastError());
+        count(ctx, 1, 0, 0);
+        return VKT_BCN_OK;
+    }
     const size_t row_bytes = size_t(ow) * comps * sizeof(float);
     // output-row bands whose input-row span fits the budget (at least one output row per band)
     uint32_t y0 = out_y0;
