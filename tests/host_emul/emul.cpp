@@ -142,6 +142,7 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
     static bool once6 = (vkt::bc7_m6_reduced_build(m6_reduced), true);
     (void) once6;
     kp.m6_reduced = m6_reduced;
+    kp.opt7 = &tables.opt7[0][0];
     const bool perceptual = params->perceptual != 0;
     auto work = [&](uint64_t b0, uint64_t b1) {
         vkt::Texel column[16];

@@ -308,6 +308,7 @@ struct Bc7KernelParams
     uint64_t forced_sel;       // m_selectors[16], one nibble per cell element
     float low_freq_weight;     // bc7enc.cpp:1819
     const uint8_t *m6_reduced; // g_mode6_reduced_quant[2048][2] (bc7enc.cpp:188-211) in device memory, [value][p]
+    const uint32_t *opt7;      // Bc7Tables::opt7 where the kernel can read it (global memory on the device: the table stays out of shared memory)
 };
 
 // Kernel variant (template parameter KV of everything below):
@@ -487,11 +488,11 @@ VKT_FN uint64_t solid_cell(const Bc7Tables &T, const Bc7KernelParams &P, Lane<ST
 #pragma unroll
         for(uint32_t p = 0; p < 4; ++p)
         {
-            const uint32_t err = (T.opt7[r][p] & 0xFFFF) + (T.opt7[g][p] & 0xFFFF) + (T.opt7[b][p] & 0xFFFF) + (T.opt7[a][p] & 0xFFFF);
+            const uint32_t err = (P.opt7[r * 4 + p] & 0xFFFF) + (P.opt7[g * 4 + p] & 0xFFFF) + (P.opt7[b * 4 + p] & 0xFFFF) + (P.opt7[a * 4 + p] & 0xFFFF);
             if(err < best_err) { best_err = err, best_p = p; }
         }
         const uint32_t hp = best_p >> 1, lp = best_p & 1;
-        const uint32_t er = T.opt7[r][best_p], eg = T.opt7[g][best_p], eb = T.opt7[b][best_p], ea = T.opt7[a][best_p];
+        const uint32_t er = P.opt7[r * 4 + best_p], eg = P.opt7[g * 4 + best_p], eb = P.opt7[b * 4 + best_p], ea = P.opt7[a * 4 + best_p];
         out.lo = pack4((er >> 16) & 255, (eg >> 16) & 255, (eb >> 16) & 255, (ea >> 16) & 255);
         out.hi = pack4(er >> 24, eg >> 24, eb >> 24, ea >> 24);
         out.pbits = lp | (hp << 1);

@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(256) bc7_classify_kernel(const __grid_constant
     }
 }
 
-__host__ __device__ constexpr size_t bc7_smem_table_bytes(bool alpha) { return alpha ? sizeof(Bc7Tables) : offsetof(Bc7Tables, opt7); }
+// (the mode-7 single-colour table at the end of Bc7Tables is read from global memory through Bc7KernelParams::opt7: 16 loads per
+// mode-7 cell, and 4 KB less shared memory per CTA)
+__host__ __device__ constexpr size_t bc7_smem_table_bytes(bool) { return offsetof(Bc7Tables, opt7); }
 static_assert(offsetof(Bc7Tables, opt7) % 16 == 0, "table prefix is copied as uint4");
 
 // One lane == one block of the work list (list == nullptr: every block of the launch, in order).
@@ -463,6 +465,7 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
                              "must exist in every enabled mode's palette; 0 <= low_frequency_partition_weight <= 65536)");
     }
     kp.m6_reduced = reinterpret_cast<const uint8_t *>(s->d_tables + 1);
+    kp.opt7 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s->d_tables) + offsetof(Bc7Tables, opt7));
     for(uint32_t first = 0; first < num_images; first += kBc7MaxImages)
     {
         Bc7Batch B = {};
