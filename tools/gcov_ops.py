@@ -43,6 +43,7 @@ CONFIGS = {
     "c2": dict(base=4096, kind=0, uber=0, parts=64, fb=1),
     "c3": dict(base=8192, kind=1, uber=0, parts=64, fb=0),
     "c5": dict(base=16384, kind=0, uber=4, parts=64, fb=0),
+    "c4_alpha": dict(base=4096, kind=1, uber=0, parts=64, fb=1),  # the every-fourth texture of the material batch
 }
 LINES = {"D_rgb": 802, "D_rgba": 790, "pal_ch": 686, "eval": 645, "E1": 1505, "E7": 1648, "S1": 1443, "S7": 1581, "part": 1801,
          "ccc": 1101, "n_mean": 1149, "n_cov": 1186, "n_ipca": 1164, "fos": 868, "ls_rgb": 351, "n_ls_rgb": 364, "ls_rgba": 287,
@@ -138,7 +139,7 @@ def ops_from_events(n: int, e: dict, alpha: bool) -> tuple[float, dict]:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c1,c2,c3,c5")
+    ap.add_argument("--configs", default="c1,c2,c3,c5,c4_alpha")
     ap.add_argument("--blocks", type=int, default=120000)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "gcov_ops.json"))
     a = ap.parse_args()
@@ -174,6 +175,11 @@ def main():
                 "levels_sampled": [{"level": l, "level_blocks": lb, "sampled": s} for l, lb, s in weights],
             }
             print(name, f"{n} blocks ({n_a} alpha): {ops:.0f} ops/block = {ops / 16:.0f} ops/pixel (opaque {ops_o:.0f}, alpha {ops_a:.0f})", flush=True)
+    cfgs = result["configs"]
+    if "c2" in cfgs and "c4_alpha" in cfgs:  # C4: three opaque textures (as C2) to one with alpha gradients, all at defaults
+        ops = 0.75 * cfgs["c2"]["ops_per_block"] + 0.25 * cfgs["c4_alpha"]["ops_per_block"]
+        cfgs["c4"] = {"input": "material batch: 3 x (4096x4096 kind 0) : 1 x (4096x4096 kind 1), defaults -- 0.75 c2 + 0.25 c4_alpha",
+                      "blocks": cfgs["c2"]["blocks"] + cfgs["c4_alpha"]["blocks"], "ops_per_block": ops, "ops_per_pixel": ops / 16.0}
     with open(a.out, "w") as f:
         json.dump(result, f, indent=1)
     print("wrote", a.out)
