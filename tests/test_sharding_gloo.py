@@ -146,3 +146,86 @@ def test_sharded_chain_gathers_to_the_single_worker_result(port_oracle):
     ok, tmax = q.get(timeout=5)
     assert ok
     assert tmax == float(world)
+
+
+def _shared_chain_worker(rank, world, port, q):
+    """One worker of the strong-scaling driver's host side (bench_strong.SharedChain + hostshare.FlagBarrier), on CPU: the
+    oracle stands in for the GPU, everything else -- shared source filled by rows, shared level arrays written in place at
+    the C-ABI shard rows, hand-over of the last sliced level, flag barrier -- is the code the bench runs."""
+    import torch.distributed as dist
+    import bench_strong
+    from oracle import pyoracle
+    from vierkant_b200 import capi
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H = 256, 1024  # levels 1024, 512 and 256 rows are sliced over two workers, the tail is worker 0's
+        sc = bench_strong.SharedChain(f"vkt_test_{port}", W, H, world, rank, dist.barrier)
+        try:
+            synth.fill_shared(sc.bufs["src"].path, 0, W, H, 1, 77, (H * rank // world, H * (rank + 1) // world), procs=2)
+            dist.barrier()
+            oracle = pyoracle.PortOracle()
+            M = int(sc.sp.sliced_levels)
+            assert M >= 2 and int(sc.sp.workers) == world
+            # every worker derives the level images (the cheap part) and writes ONLY its own block rows of the sliced levels
+            px, prev = [], np.ascontiguousarray(sc.src)
+            for (lw, lh) in sc.level_dims:
+                prev = oracle.resize(prev, lw, lh)
+                px.append(prev)
+            for l in range(M):
+                r0, r1 = capi.shard_rows(W, H, True, rank, world, l)
+                bx = sc.level_dims[l][0] // 4
+                sc.levels[l][r0 * bx:r1 * bx] = oracle.encode_blocks(synth.to_blocks(np.ascontiguousarray(px[l][4 * r0:4 * r1])))
+            # hand-over: this worker's pixel rows of the last sliced level, then the flag barrier (no data moves through it)
+            lw, lh = sc.level_dims[M - 1]
+            r0, r1 = capi.shard_rows(W, H, True, rank, world, M - 1)
+            hand = sc.handover[:lw * lh * 4].reshape(lh, lw, 4)
+            hand[4 * r0:4 * r1] = px[M - 1][4 * r0:4 * r1]
+            sc.barrier.arrive(1)
+            if rank == 0:
+                sc.barrier.wait_all(1, timeout_s=60)
+                prev = np.ascontiguousarray(hand)  # every worker's rows are in place now
+                for l in range(M, sc.L):
+                    prev = oracle.resize(prev, *sc.level_dims[l])
+                    sc.levels[l][:] = oracle.encode_blocks(synth.to_blocks(prev))
+            sc.barrier.arrive(2)
+            sc.barrier.wait_all(2, timeout_s=60)
+            if rank == 0:
+                want = oracle.compress(synth.make_texture(W, H, 1, seed=77), 1, True)
+                ok = all(np.array_equal(a, b) for a, b in zip(sc.levels, want["levels"]))
+                q.put(bool(ok))
+            dist.barrier()
+        finally:
+            sc.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_chain_and_flag_barrier_gather_one_chain(port_oracle, cuda_lib):
+    """world_size 2, gloo: the shared-memory gather of bench_strong (one chain, block rows written in place by their owners,
+    tail levels by worker 0 after the flag barrier) reproduces the single-worker chain byte for byte."""
+    import torch.multiprocessing as mp
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shared_chain_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_fill_shared_matches_make_texture(tmp_path):
+    from vierkant_b200 import hostshare
+    buf = hostshare.SharedBuffer(f"vkt_test_fill_{os.getpid()}", 64 * 200 * 4, True)
+    try:
+        synth.fill_shared(buf.path, 0, 64, 200, 1, 9, (0, 120), procs=3)
+        synth.fill_shared(buf.path, 0, 64, 200, 1, 9, (120, 200), procs=1)
+        assert np.array_equal(buf.array.reshape(200, 64, 4), synth.make_texture(64, 200, 1, seed=9))
+    finally:
+        buf.close()

@@ -479,7 +479,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         bool encode;    // false: halo rows, resized here only because this device's slices of the next levels read them
     };
     // graded split of the block rows [r0, r1): 1, 2, 3, 4 ... 4, 3, 2, 1 thirty-seconds when there is enough work
-    auto graded = [&](uint32_t r0, uint32_t r1, std::vector<Band> &out) {
+    auto graded = [&](uint32_t r0, uint32_t r1, std::vector<Band> &out, bool resident) {
         static const uint8_t kBig[] = {1, 3, 6, 10, 14, 18, 22, 26, 29, 31, 32};// cumulative 32nds
         static const uint8_t kQuarters[] = {8, 16, 24, 32};
         static const uint8_t kMid[] = {16, 32};
@@ -487,7 +487,9 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         // measured (profiles/r1_ss_sweep.txt): a band needs enough CTAs to be worth its launches and its block latency --
         // 4096^2 wants the graded schedule, 2048^2 four equal bands (1.09 -> 1.00 ms), 1024^2 two, 512^2 one (0.32 -> 0.28 ms)
         const uint64_t blocks = uint64_t(r1 - r0) * (plan.level_width[0] / 4);
-        const bool big = blocks >= (1u << 19), quarters = blocks >= (1u << 17), mid = blocks >= (1u << 15);
+        // (a source that already lives on the device has no upload to hide: two bands, so that the encoder starts after half of the
+        // level-0 resize, instead of the graded schedule whose small first and last bands cannot fill the device)
+        const bool big = !resident && blocks >= (1u << 19), quarters = !resident && blocks >= (1u << 17), mid = blocks >= (1u << 15);
         const uint8_t *f = big ? kBig : (quarters ? kQuarters : (mid ? kMid : kOne));
         size_t nf = big ? sizeof(kBig) : (quarters ? sizeof(kQuarters) : (mid ? sizeof(kMid) : sizeof(kOne)));
         // tuning experiments only: VKT_BCN_BANDS="2,8,16,24,30,32" (cumulative 32nds) replaces the schedule
@@ -601,7 +603,7 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         // rows above and below (resized only).  Source rows are uploaded in the same order, each band fetching just the
         // rows its resize taps reach that are not on the device yet.
         std::vector<Band> bands;
-        graded(own[0].first, own[0].second, bands);
+        graded(own[0].first, own[0].second, bands, src_in_place);
         if(need[0].second > own[0].second * 4) { bands.push_back({own[0].second * 4, need[0].second, false}); }
         if(need[0].first < own[0].first * 4) { bands.push_back({need[0].first, own[0].first * 4, false}); }
         const uint32_t K = uint32_t(bands.size());
