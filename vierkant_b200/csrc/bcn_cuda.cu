@@ -315,7 +315,7 @@ struct DeviceSlot
 struct vkt_bcn_ctx
 {
     std::vector<vkt::DeviceSlot *> slots;
-    std::vector<vkt::DeviceSlot *> slots2;// second set of streams / buffers per device (compress_batch), made on first use
+    std::vector<vkt::DeviceSlot *> slots2;// further sets of streams / buffers per device (compress_batch lanes; entry k: device k % G), made on first use
     vkt::Bc7Tables host_tables;
     std::string last_error;
     std::mutex err_mtx;

@@ -954,22 +954,29 @@ static int compress_many(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32
     std::vector<std::unique_lock<std::mutex>> locks;
     for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
     const size_t G = ctx->slots.size();
-    while(ctx->slots2.size() < G)
+    // Lanes per device: two for large textures (the next texture's upload and resizes run under the current one's kernels); a
+    // 1024^2 chain is one wave of blocks and spends most of its 0.4 ms waiting for block latencies, so small textures get four
+    // lanes -- four chains in flight per device keep it full (measured: profiles/r2_s_batch_lanes.txt).
+    uint64_t max_px = 0;
+    for(uint32_t t = 0; t < n; ++t) { max_px = std::max<uint64_t>(max_px, uint64_t(sources[t].width) * sources[t].height); }
+    size_t per_device = (max_px <= (uint64_t(1) << 22)) ? 4 : 2;
+    if(const char *e = getenv("VKT_BCN_BATCH_LANES")) { per_device = size_t(std::max(1, std::min(8, atoi(e)))); }// (tuning)
+    while(ctx->slots2.size() < (per_device - 1) * G)
     {
         auto *s = new DeviceSlot;
-        s->device = ctx->slots[ctx->slots2.size()]->device;
+        s->device = ctx->slots[ctx->slots2.size() % G]->device;
         const cudaError_t e = init_slot(s, ctx->host_tables);
         if(e != cudaSuccess)
         {
             // a half-made lane must not be found by the next call
             const int dev = s->device;
             destroy_slot(s);
-            return fail(ctx, VKT_BCN_ERR_CUDA, "second lane of device %d: %s", dev, cudaGetErrorString(e));
+            return fail(ctx, VKT_BCN_ERR_CUDA, "extra lane of device %d: %s", dev, cudaGetErrorString(e));
         }
         ctx->slots2.push_back(s);
     }
     std::vector<std::vector<DeviceSlot *>> lanes;// lane k: device k % G, set k / G
-    for(size_t k = 0; k < 2 * G; ++k) { lanes.push_back({(k < G) ? ctx->slots[k] : ctx->slots2[k - G]}); }
+    for(size_t k = 0; k < per_device * G; ++k) { lanes.push_back({(k < G) ? ctx->slots[k] : ctx->slots2[k - G]}); }
     std::vector<char> busy(lanes.size(), 0);
     int rc = VKT_BCN_OK;
     for(uint32_t t = 0; t < n && !rc; ++t)
