@@ -540,7 +540,14 @@ def main():
         if name not in bench_strong.STRONG:
             continue
         # release the headline's buffers first?  They are small (0.6 GB); the C5 chain needs ~4 GB of the 180 GB per GPU.
-        rep = bench_strong.run_strong(name, ctx, rank, world, dev, args, dist, base=args.strong_base, check=not args.no_cpu_baseline)
+        try:
+            rep = bench_strong.run_strong(name, ctx, rank, world, dev, args, dist, base=args.strong_base, check=not args.no_cpu_baseline,
+                                          clock_sampler=ClockSampler(local) if rank == 0 else None)
+        except Exception as e:  # noqa: BLE001 -- the strong arm must never take the headline line down
+            rep = {"error": repr(e)}
+            if rank == 0:
+                strong[name] = rep
+            break  # the ranks are out of step now: no further collective work
         if rank == 0:
             strong[name] = rep
 

@@ -127,7 +127,8 @@ def reference_sample(cfg_name: str, cfg: dict, src: np.ndarray, got_levels: list
                                 "what": "bc7enc_compress_block over the sampled blocks (pre-filtered), row partition over host threads"}}
 
 
-def run_strong(cfg_name: str, ctx: capi.BcnContext, rank: int, world: int, dev, args, dist, base: int | None = None, check: bool = True):
+def run_strong(cfg_name: str, ctx: capi.BcnContext, rank: int, world: int, dev, args, dist, base: int | None = None, check: bool = True,
+               clock_sampler=None):
     """One strong-scaling config on `world` ranks.  Returns the report dict on rank 0, None elsewhere."""
     import torch
     cfg = STRONG[cfg_name]
@@ -191,8 +192,11 @@ def run_strong(cfg_name: str, ctx: capi.BcnContext, rank: int, world: int, dev, 
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t[0]) / steps, {k: (s1[k] - s0[k]) // steps for k in s0}
 
+        if clock_sampler is not None:  # rank 0: SM clocks / throttle reasons over both timed regions (seconds long for C5)
+            clock_sampler.start()
         ms_res, st_res = timed(lambda: step(d_src, dev_ptrs))
         ms_e2e, st_e2e = timed(lambda: step(sc.src, host_ptrs))
+        clocks = clock_sampler.stop() if clock_sampler is not None else None
         # per-rank traffic of the gathered run, summed over the job
         tr = torch.tensor([st_e2e["h2d_bytes"], st_e2e["d2h_bytes"], st_res["kernel_launches"]], dtype=torch.float64, device=dev)
         if world > 1:
@@ -252,6 +256,7 @@ def run_strong(cfg_name: str, ctx: capi.BcnContext, rank: int, world: int, dev, 
                                  f"levels {int(sc.sp.sliced_levels)}..{L - 1} on rank 0 from a {int(sc.sp.handover_bytes)} B host hand-over; no collective"
                                  if int(sc.sp.workers) > 1 else "one rank encodes the whole chain"),
                 "timing": "CUDA events around K lockstep chains (every call waits for its own GPU work), max with the host clock, max over ranks",
+                "clocks": clocks,
             }
             try:  # ALU roofline of the whole job: gcov-pinned ops per pixel x pixel rate / (N x issue peak)
                 import json

@@ -96,7 +96,13 @@ compress_result_t compress(const compress_info_t &compress_info)
     // the vectors up front, src/texture_block_compression.cpp:88-96 -- in front of the first upload that is pure latency).
     auto alloc_level = [](void *user, uint32_t level, size_t bytes) -> void * {
         auto &levels = *static_cast<std::vector<std::vector<block_t>> *>(user);
-        levels[level].resize(bytes / sizeof(block_t));
+        try
+        {
+            levels[level].resize(bytes / sizeof(block_t));
+        } catch(...)// (no exception may cross the C ABI, least of all on the library's helper thread: null = out of memory)
+        {
+            return nullptr;
+        }
         return levels[level].data();
     };
     // bc7enc_compress_block_params_init() defaults, as the reference uses them (:73-74); NULL selects them

@@ -74,13 +74,13 @@ class FlagBarrier:
     def arrive(self, phase: int):
         self.flags[self.rank, 0] = phase
 
-    def wait_all(self, phase: int, timeout_s: float = 600.0):
+    def wait_all(self, phase: int, timeout_s: float = 180.0):
         t0 = time.monotonic()
         while int(self.flags[:, 0].min()) < phase:
             if time.monotonic() - t0 > timeout_s:
                 raise TimeoutError(f"worker {self.rank}: barrier phase {phase} not reached by all workers")
 
-    def wait_for(self, other: int, phase: int, timeout_s: float = 600.0):
+    def wait_for(self, other: int, phase: int, timeout_s: float = 180.0):
         t0 = time.monotonic()
         while int(self.flags[other, 0]) < phase:
             if time.monotonic() - t0 > timeout_s:
