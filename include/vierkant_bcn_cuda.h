@@ -16,7 +16,9 @@
  *   - there is NO CPU fallback: without a usable CUDA device every call fails with VKT_BCN_ERR_NO_DEVICE
  *   - output blocks are bit-identical to the reference's (same inputs, same parameters); block order is row-major,
  *     blocks[bx + by * (width / 4)], 16 bytes each (vierkant::bcn::block_t, texture_block_compression.hpp:22-25)
- *   - a context may be used from several host threads at once (calls are serialised per device slot)
+ *   - a context may be used from several host threads at once: on a single-device context concurrent vkt_bcn_cuda_compress /
+ *     _compress_alloc calls run on up to four lanes of the device (own streams and buffers each), so a loader that fans its
+ *     textures out over threads overlaps their uploads, kernels and downloads; every other call is serialised per device slot
  */
 #ifndef VIERKANT_BCN_CUDA_H
 #define VIERKANT_BCN_CUDA_H

@@ -315,7 +315,8 @@ struct DeviceSlot
 struct vkt_bcn_ctx
 {
     std::vector<vkt::DeviceSlot *> slots;
-    std::vector<vkt::DeviceSlot *> slots2;// further sets of streams / buffers per device (compress_batch lanes; entry k: device k % G), made on first use
+    std::vector<vkt::DeviceSlot *> slots2;// further sets of streams / buffers per device (lanes; entry k: device k % G), made on first use
+    std::mutex lanes_mtx;                  // guards slots2 (its size and its growth); never held while a slot mutex is waited for
     vkt::Bc7Tables host_tables;
     std::string last_error;
     std::mutex err_mtx;

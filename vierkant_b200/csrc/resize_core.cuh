@@ -883,17 +883,87 @@ static int chain_wait(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slots)
     return rc;
 }
 
+// Lanes.  A slot (streams, buffers, tables, axis cache) carries one chain at a time.  A single-device context answers concurrent
+// compress() calls from several host threads -- a loader that fans its textures out -- on different lanes of the device, up to
+// kMaxLanes, so their uploads, kernels and downloads overlap like the textures of a compress_batch call; only when every lane is
+// busy does a call wait.  Lock order everywhere: primary slots in index order, then slots2 in index order.
+constexpr size_t kMaxLanes = 4;
+
+// make sure slots2 holds at least `want` entries (entry k: device k % G)
+static int grow_lanes(vkt_bcn_ctx *ctx, size_t want)
+{
+    std::lock_guard<std::mutex> g(ctx->lanes_mtx);
+    const size_t G = ctx->slots.size();
+    if(ctx->slots2.capacity() < 64) { ctx->slots2.reserve(64); }// entries are never moved once published
+    while(ctx->slots2.size() < want && ctx->slots2.size() < 64)
+    {
+        auto *s = new DeviceSlot;
+        s->device = ctx->slots[ctx->slots2.size() % G]->device;
+        const cudaError_t e = init_slot(s, ctx->host_tables);
+        if(e != cudaSuccess)
+        {
+            // a half-made lane must not be found by the next call
+            const int dev = s->device;
+            destroy_slot(s);
+            return fail(ctx, VKT_BCN_ERR_CUDA, "extra lane of device %d: %s", dev, cudaGetErrorString(e));
+        }
+        ctx->slots2.push_back(s);
+    }
+    return VKT_BCN_OK;
+}
+
+static size_t lane_count(vkt_bcn_ctx *ctx)
+{
+    std::lock_guard<std::mutex> g(ctx->lanes_mtx);
+    return ctx->slots2.size();
+}
+
+// a free lane of a single-device context, locked; *slot receives it
+static int acquire_lane(vkt_bcn_ctx *ctx, DeviceSlot **slot, std::unique_lock<std::mutex> *lock)
+{
+    for(;;)
+    {
+        const size_t extra = lane_count(ctx);
+        for(size_t k = 0; k <= extra; ++k)
+        {
+            DeviceSlot *s = k ? ctx->slots2[k - 1] : ctx->slots[0];
+            std::unique_lock<std::mutex> l(s->mtx, std::try_to_lock);
+            if(l.owns_lock())
+            {
+                *slot = s, *lock = std::move(l);
+                return VKT_BCN_OK;
+            }
+        }
+        if(extra + 1 >= kMaxLanes) { break; }
+        const int rc = grow_lanes(ctx, extra + 1);
+        if(rc) { return rc; }
+    }
+    *slot = ctx->slots[0];// every lane is busy: queue up behind the primary one
+    *lock = std::unique_lock<std::mutex>(ctx->slots[0]->mtx);
+    return VKT_BCN_OK;
+}
+
 // The whole of vierkant::bcn::compress() for one image on every device of the context.
 static int compress_chain(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t comps,
                           int generate_mipmaps, const vkt_bc7_params *params, void *const *level_blocks)
 {
     std::vector<std::unique_lock<std::mutex>> locks;
-    for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    std::vector<DeviceSlot *> use(ctx->slots);
+    if(ctx->slots.size() == 1)
+    {
+        locks.emplace_back();
+        const int rl = acquire_lane(ctx, &use[0], &locks[0]);
+        if(rl) { return rl; }
+    }
+    else
+    {
+        for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    }
     std::vector<std::pair<cudaEvent_t, std::string>> marks;
     const auto h0 = std::chrono::steady_clock::now();
-    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, &marks);
+    int rc = chain_enqueue(ctx, use, mode, pixels, width, height, comps, generate_mipmaps, params, level_blocks, &marks);
     const auto h1 = std::chrono::steady_clock::now();
-    const int rw = chain_wait(ctx, ctx->slots);
+    const int rw = chain_wait(ctx, use);
     if(!rc) { rc = rw; }
     if(!marks.empty() && ctx->slots.size() == 1)// VKT_BCN_TRACE=1
     {
@@ -919,12 +989,32 @@ static int compress_chain_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *
     vkt_bcn_plan plan;
     if(vkt_bcn_cuda_compress_plan(width, height, generate_mipmaps, &plan)) { return fail(ctx, VKT_BCN_ERR_INVALID, "bad size"); }
     std::vector<std::unique_lock<std::mutex>> locks;
-    for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    std::vector<DeviceSlot *> use(ctx->slots);
+    if(ctx->slots.size() == 1)
+    {
+        locks.emplace_back();
+        const int rl = acquire_lane(ctx, &use[0], &locks[0]);
+        if(rl) { return rl; }
+    }
+    else
+    {
+        for(DeviceSlot *s: ctx->slots) { locks.emplace_back(s->mtx); }
+    }
     // The allocator runs on a helper thread while this one queues the chain (with a pageable source the queueing itself is
     // host work: the source rows are staged band by band): level 0 first, one call at a time.
     uint8_t *base[16] = {};
     uint32_t failed_level = ~0u;
+    static const bool trace = getenv("VKT_BCN_TRACE") != nullptr;
+    const auto h0 = std::chrono::steady_clock::now();
+    double alloc_ms = 0.0;
     std::thread allocator([&] {
+        const auto a0 = std::chrono::steady_clock::now();
+        struct Done
+        {
+            double *ms;
+            std::chrono::steady_clock::time_point t0;
+            ~Done() { *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+        } done{&alloc_ms, a0};
         for(uint32_t l = 0; l < plan.num_levels; ++l)
         {
             base[l] = static_cast<uint8_t *>(alloc_level(user, l, size_t(plan.level_num_blocks[l]) * 16));
@@ -935,14 +1025,23 @@ static int compress_chain_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *
             }
         }
     });
-    int rc = chain_enqueue(ctx, ctx->slots, mode, pixels, width, height, comps, generate_mipmaps, params, nullptr, nullptr);
+    int rc = chain_enqueue(ctx, use, mode, pixels, width, height, comps, generate_mipmaps, params, nullptr, nullptr);
+    const auto h1 = std::chrono::steady_clock::now();
     allocator.join();
+    const auto h2 = std::chrono::steady_clock::now();
     if(!rc && failed_level != ~0u) { rc = fail(ctx, VKT_BCN_ERR_OOM, "the caller's allocator returned null for level %u", failed_level); }
-    for(DeviceSlot *s: ctx->slots)
+    for(DeviceSlot *s: use)
     {
         for(DeviceSlot::PendingCopy &pc: s->pending) { pc.dst = (!rc && base[pc.level]) ? base[pc.level] + pc.offset : nullptr; }
     }
-    const int rw = chain_wait(ctx, ctx->slots);
+    const int rw = chain_wait(ctx, use);
+    if(trace)
+    {
+        const auto h3 = std::chrono::steady_clock::now();
+        auto ms = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - h0).count(); };
+        fprintf(stderr, "[vkt trace] compress_alloc host: queued after %.3f ms, allocator took %.3f ms (joined at %.3f), done at %.3f ms\n", ms(h1), alloc_ms,
+                ms(h2), ms(h3));
+    }
     return rc ? rc : rw;
 }
 
@@ -961,20 +1060,11 @@ static int compress_many(vkt_bcn_ctx *ctx, const vkt_bcn_source *sources, uint32
     for(uint32_t t = 0; t < n; ++t) { max_px = std::max<uint64_t>(max_px, uint64_t(sources[t].width) * sources[t].height); }
     size_t per_device = (max_px <= (uint64_t(1) << 22)) ? 4 : 2;
     if(const char *e = getenv("VKT_BCN_BATCH_LANES")) { per_device = size_t(std::max(1, std::min(8, atoi(e)))); }// (tuning)
-    while(ctx->slots2.size() < (per_device - 1) * G)
     {
-        auto *s = new DeviceSlot;
-        s->device = ctx->slots[ctx->slots2.size() % G]->device;
-        const cudaError_t e = init_slot(s, ctx->host_tables);
-        if(e != cudaSuccess)
-        {
-            // a half-made lane must not be found by the next call
-            const int dev = s->device;
-            destroy_slot(s);
-            return fail(ctx, VKT_BCN_ERR_CUDA, "extra lane of device %d: %s", dev, cudaGetErrorString(e));
-        }
-        ctx->slots2.push_back(s);
+        const int rg = grow_lanes(ctx, (per_device - 1) * G);
+        if(rg) { return rg; }
     }
+    for(size_t k = 0; k < (per_device - 1) * G; ++k) { locks.emplace_back(ctx->slots2[k]->mtx); }// (entries are stable once published)
     std::vector<std::vector<DeviceSlot *>> lanes;// lane k: device k % G, set k / G
     for(size_t k = 0; k < per_device * G; ++k) { lanes.push_back({(k < G) ? ctx->slots[k] : ctx->slots2[k - G]}); }
     std::vector<char> busy(lanes.size(), 0);
