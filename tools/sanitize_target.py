@@ -22,4 +22,27 @@ with capi.BcnContext([0]) as ctx:
     ctx.compress(synth.make_texture(2 * n if n < 2048 else n, n, 1), capi.MODE_BC7, True)
     ctx.compress(b, capi.MODE_BC7, True)
     ctx.compress_batch([a, b, a[..., :3]], [capi.MODE_BC7, capi.MODE_BC5, capi.MODE_BC7], True)
+    # round 2: deferred destinations, the fused resize (>= 2^20 output samples per call), concurrent calls on lanes, a process shard
+    ctx.compress_alloc(b, capi.MODE_BC7, True)
+    if os.environ.get("VKT_SAN_BIG"):
+        ctx.compress_alloc(synth.make_texture(2048, 1024, 0), capi.MODE_BC7, True)
+    import threading
+    ts = [threading.Thread(target=lambda im=im: ctx.compress(im, capi.MODE_BC7, True)) for im in (a, b, a, b)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    import ctypes as C
+    import numpy as np
+    plan = capi.compress_plan(256, 128, True)
+    lv = [np.zeros((int(plan.level_num_blocks[l]), 16), dtype=np.uint8) for l in range(plan.num_levels)]
+    ptrs = (C.c_void_p * plan.num_levels)(*[x.ctypes.data for x in lv])
+    hand = np.zeros(max(int(capi.shard_plan(256, 128, True, 2).handover_bytes), 1), dtype=np.uint8)
+    workers = [capi.BcnContext([0]) for _ in range(2)]
+    for r, w in enumerate(workers):
+        w.compress_shard_begin(capi.MODE_BC7, a, 256, 128, 4, True, None, r, 2, ptrs, hand)
+    for r, w in enumerate(workers):
+        w.compress_shard_end(capi.MODE_BC7, a, 256, 128, 4, True, None, r, 2, ptrs, hand)
+    for w in workers:
+        w.close()
 print("ok")

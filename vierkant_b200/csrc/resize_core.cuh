@@ -1007,7 +1007,7 @@ static int compress_chain_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *
     static const bool trace = getenv("VKT_BCN_TRACE") != nullptr;
     const auto h0 = std::chrono::steady_clock::now();
     double alloc_ms = 0.0;
-    std::thread allocator([&] {
+    auto allocate_all = [&] {
         const auto a0 = std::chrono::steady_clock::now();
         struct Done
         {
@@ -1024,10 +1024,20 @@ static int compress_chain_alloc(vkt_bcn_ctx *ctx, uint32_t mode, const uint8_t *
                 return;
             }
         }
-    });
+    };
+    std::thread allocator;
+    bool threaded = true;
+    try
+    {
+        allocator = std::thread(allocate_all);
+    } catch(...)// (no thread to be had: allocate after queueing, on this one)
+    {
+        threaded = false;
+    }
     int rc = chain_enqueue(ctx, use, mode, pixels, width, height, comps, generate_mipmaps, params, nullptr, nullptr);
     const auto h1 = std::chrono::steady_clock::now();
-    allocator.join();
+    if(threaded) { allocator.join(); }
+    else { allocate_all(); }
     const auto h2 = std::chrono::steady_clock::now();
     if(!rc && failed_level != ~0u) { rc = fail(ctx, VKT_BCN_ERR_OOM, "the caller's allocator returned null for level %u", failed_level); }
     for(DeviceSlot *s: use)
