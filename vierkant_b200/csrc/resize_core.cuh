@@ -603,7 +603,10 @@ static int chain_enqueue(vkt_bcn_ctx *ctx, const std::vector<DeviceSlot *> &slot
         // rows above and below (resized only).  Source rows are uploaded in the same order, each band fetching just the
         // rows its resize taps reach that are not on the device yet.
         std::vector<Band> bands;
-        graded(own[0].first, own[0].second, bands, src_in_place);
+        // (two bands only when nothing crosses the link in either direction: host destinations still want their downloads hidden)
+        bool dst_on_device = !any_stage_out;
+        for(uint32_t l = 0; l < plan.num_levels && dst_on_device && !deferred; ++l) { dst_on_device = device_pointer_on(level_blocks[l], s->device); }
+        graded(own[0].first, own[0].second, bands, src_in_place && dst_on_device && !deferred);
         if(need[0].second > own[0].second * 4) { bands.push_back({own[0].second * 4, need[0].second, false}); }
         if(need[0].first < own[0].first * 4) { bands.push_back({need[0].first, own[0].first * 4, false}); }
         const uint32_t K = uint32_t(bands.size());
