@@ -9,6 +9,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../vierkant_b200/csrc/bc5_core.cuh"
 #include "../../vierkant_b200/csrc/bc7_core.cuh"
 #include "../../vierkant_b200/csrc/bc7_params.h"
 #include "../../vierkant_b200/csrc/chain_plan.h"
@@ -102,6 +103,37 @@ int emul_resize_decode_mismatches()
         bad += vkt::resize_decode_u8(v) != want;
     }
     return bad;
+}
+
+// BC4 selector count: the reciprocal multiplication of bc5_core.cuh against the seven threshold compares of rgbcx
+// (rgbcx.cpp:2655-2683), for every delta and every reachable numerator.  Returns the number of disagreements.
+int emul_bc4_count_mismatches()
+{
+    int bad = 0;
+    for(uint32_t delta = 1; delta <= 255; ++delta)
+    {
+        const uint32_t recip = vkt::bc4_reciprocal(delta);
+        for(uint32_t x = 0; x <= 14u * 255u + 4u; ++x)
+        {
+            const int xi = int(x), d = int(delta);
+            const uint32_t want = uint32_t((xi >= d * 13) + (xi >= d * 11) + (xi >= d * 9) + (xi >= d * 7) + (xi >= d * 5) + (xi >= d * 3) + (xi >= d));
+            bad += vkt::bc4_count(x + delta, recip) != want;
+        }
+    }
+    return bad;
+}
+
+// the device-side BC5 block encoder as host code: tiles (n, 16, 4) -> (n, 16) bytes
+void emul_bc5_encode_blocks(const uint8_t *px, uint64_t num_blocks, uint8_t *out)
+{
+    for(uint64_t b = 0; b < num_blocks; ++b)
+    {
+        uint32_t t[16];
+        memcpy(t, px + 64 * b, 64);
+        const uint64_t r = vkt::bc4_encode_channel(t, 0), g = vkt::bc4_encode_channel(t, 1);
+        memcpy(out + 16 * b, &r, 8);
+        memcpy(out + 16 * b + 8, &g, 8);
+    }
 }
 
 // number of (max, ly, hy) cells whose compile-time uber selector map differs from the reference's float expression

@@ -250,3 +250,32 @@ def test_concurrent_compress_calls_run_on_lanes(ctx):
             assert all(np.array_equal(x, y) for x, y in zip(a, b))
     print(f"8 x 1024^2 chains: sequential {sequential * 1e3:.2f} ms, four threads {best * 1e3:.2f} ms")
     assert best < sequential  # (pageable numpy buffers on both sides: the staging copies overlap too)
+
+
+def test_bc5_edge_cases_against_the_reference(ctx, ref_oracle):
+    """The BC5 kernel's packed two-channel arithmetic (bc5_core.cuh: reciprocal count, 16x2 SIMD halves) on what could break it:
+    flat channels (either or both), two-valued channels, every delta from 1 to 255 with values at both ends and in between,
+    random noise, and a big synthetic texture -- against rgbcx::encode_bc5 of the unmodified reference."""
+    rng = np.random.default_rng(23)
+    tiles = [rng.integers(0, 256, size=(6000, 16, 4), dtype=np.uint8)]
+    flat = rng.integers(0, 256, size=(1500, 16, 4), dtype=np.uint8)
+    flat[:500, :, 0] = flat[:500, :1, 0]            # R flat
+    flat[500:1000, :, 1] = flat[500:1000, :1, 1]    # G flat
+    flat[1000:, :, :2] = flat[1000:, :1, :2]        # both flat
+    tiles.append(flat)
+    tiles.append((rng.integers(0, 2, size=(1500, 16, 4)) * rng.integers(1, 256, size=(1500, 1, 4))).astype(np.uint8))
+    ramps = np.zeros((255 * 8, 16, 4), dtype=np.uint8)  # every delta, shifted to eight different minima
+    for d in range(1, 256):
+        for k in range(8):
+            lo = (k * (255 - d)) // 7
+            vals = lo + (np.arange(16) * d + 7) // 15
+            ramps[(d - 1) * 8 + k, :, 0] = vals
+            ramps[(d - 1) * 8 + k, :, 1] = lo + d - (vals - lo)
+    tiles.append(ramps)
+    tiles = np.ascontiguousarray(np.concatenate(tiles))
+    n = tiles.shape[0]
+    pad = (-n) % 32
+    t = np.concatenate([tiles, np.repeat(tiles[-1:], pad, axis=0)]) if pad else tiles
+    assert np.array_equal(ctx.encode_bc5(tiles_to_image(t, 32))[:n], ref_oracle.encode_bc5_blocks(tiles))
+    img = synth.make_texture(2048, 1024, 1, seed=12)
+    assert np.array_equal(ctx.encode_bc5(img), ref_oracle.encode_bc5_blocks(synth.to_blocks(img)))

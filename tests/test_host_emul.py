@@ -100,3 +100,23 @@ def test_resize_tap_lists_match_oracle(emul, port_oracle, w, h, ow, oh, c):
     """The per-output tap lists the CUDA resize passes consume (resize_axis.h), evaluated on the CPU in kernel order."""
     img = synth.make_texture(w, h, 1, seed=3 * w + h)[..., :c]
     assert np.array_equal(emul.resize(img, ow, oh), port_oracle.resize(img, ow, oh))
+
+
+def test_bc4_reciprocal_count_equals_the_threshold_compares(emul):
+    """bc5_core.cuh counts the thresholds a texel reaches with one multiplication by a rounded-up reciprocal; the reference compares
+    seven times (rgbcx.cpp:2655-2683).  Exhaustive over every delta (1..255) and every numerator the encoder can produce."""
+    assert emul.lib.emul_bc4_count_mismatches() == 0
+
+
+def test_bc5_host_build_matches_the_oracle(emul, port_oracle):
+    rng = np.random.default_rng(17)
+    tiles = np.concatenate([rng.integers(0, 256, size=(4000, 16, 4), dtype=np.uint8),
+                            np.repeat(rng.integers(0, 256, size=(500, 1, 4), dtype=np.uint8), 16, axis=1),        # solid blocks
+                            (rng.integers(0, 2, size=(1500, 16, 4)) * rng.integers(1, 256, size=(1500, 1, 4))).astype(np.uint8),  # two-valued
+                            synth.to_blocks(synth.make_texture(128, 128, 1, seed=3))])
+    tiles = np.ascontiguousarray(tiles)
+    out = np.zeros((tiles.shape[0], 16), dtype=np.uint8)
+    emul.lib.emul_bc5_encode_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    emul.lib.emul_bc5_encode_blocks.restype = None
+    emul.lib.emul_bc5_encode_blocks(tiles.ctypes.data, tiles.shape[0], out.ctypes.data)
+    assert np.array_equal(out, port_oracle.encode_bc5_blocks(tiles))
