@@ -775,6 +775,7 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
         uint32_t img, row0, row1;
         size_t in_off, out_off;
     };
+    static const uint64_t kBandBlocks = getenv("VKT_BCN_BAND_BLOCKS") ? strtoull(getenv("VKT_BCN_BAND_BLOCKS"), nullptr, 10) : (1u << 18);// (tuning; measured 2^20 / 2^18 / 2^17 / 2^16: 3.58 / 2.56 / 2.76 / 2.84 ms for a pinned 4096^2 level)
     std::vector<std::vector<Piece>> plan(G);
     std::vector<size_t> in_need(G, 0), out_need(G, 0);
     uint32_t rr = 0;
@@ -793,8 +794,17 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
             for(uint32_t g = 0; g < G; ++g)
             {
                 const uint32_t r0 = uint32_t(uint64_t(rows) * g / G), r1 = uint32_t(uint64_t(rows) * (g + 1) / G);
-                plan[g].push_back({i, r0, r1, in_need[g], out_need[g]});
-                in_need[g] += align_up((r1 - r0) * row_in, 256), out_need[g] += align_up((r1 - r0) * row_out, 256);
+                // a device's share of a large image is cut into row bands of about kBandBlocks blocks: each band is a group of
+                // its own (upload -> launch -> download on alternating streams), so the transfers of one band run under the
+                // kernels of its neighbours instead of before and after one big launch
+                const uint64_t blocks_per_row = images[i].width / 4;
+                const uint32_t band_rows = uint32_t(std::max<uint64_t>(4, (kBandBlocks + blocks_per_row - 1) / blocks_per_row));
+                for(uint32_t a = r0; a < r1; a += band_rows)
+                {
+                    const uint32_t b = std::min(r1, a + band_rows);
+                    plan[g].push_back({i, a, b, in_need[g], out_need[g]});
+                    in_need[g] += align_up((b - a) * row_in, 256), out_need[g] += align_up((b - a) * row_out, 256);
+                }
             }
         }
     }
@@ -824,7 +834,7 @@ int vkt_bcn_cuda_encode_batch(vkt_bcn_ctx *ctx, uint32_t mode, const vkt_bcn_ima
     // queue group by group, round-robin over devices so that all PCIe links start early.  A failure inside queue_group
     // only ends the queueing: the synchronise loop below still runs, so no copy into / out of the caller's buffers is in
     // flight when this call reports the error.
-    constexpr uint64_t kGroupBlocks = 1u << 20;
+    static const uint64_t kGroupBlocks = getenv("VKT_BCN_GROUP_BLOCKS") ? strtoull(getenv("VKT_BCN_GROUP_BLOCKS"), nullptr, 10) : kBandBlocks;// (tuning)
     std::vector<size_t> next(G, 0), group_no(G, 0);
     auto queue_group = [&](uint32_t g) -> int {
         DeviceSlot *s = ctx->slots[g];
