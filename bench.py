@@ -637,6 +637,32 @@ def main():
                     line["e2e_dropin"]["level0_matches_reference"] = bool(np.array_equal(lvl0, ref_levels[0]))
             except Exception as e:  # the baseline must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        if world == 1 and not args.no_cpu_baseline and "parity" not in line:
+            # the other workloads (--workload c3 | c4 | c5): the same untimed check of the e2e call's blocks against the reference
+            try:
+                if NTEX > 1:  # c4: every texture of the batch through vkt_bcn_cuda_compress_batch vs the reference's compress()
+                    oracle, kind = reference_oracle()
+                    cores = oracle.hardware_concurrency() if kind == "reference" else (os.cpu_count() or 1)
+                    ctx._check(ctx.lib.vkt_bcn_cuda_compress_batch(ctx.handle, batch_srcs[0], NTEX, 1, C.byref(params)))
+                    total = bad = 0
+                    for j in range(NTEX):
+                        want = reference_chain(oracle, kind, host_src[j].numpy(), cores)
+                        total += sum(int(a.shape[0]) for a in want)
+                        bad += sum(int((o.numpy() != np.asarray(b).reshape(-1, 16)).any(axis=1).sum()) for o, b in zip(host_out_b[j], want))
+                    line["parity"] = {"against": ("unmodified reference (oracle/_ref)" if kind == "reference" else "C port (oracle/*.c)") +
+                                                 f", vierkant::bcn::compress of each of the {NTEX} textures of the batch",
+                                      "blocks": total, "mismatched_blocks": bad, "bit_exact": bad == 0}
+                elif args.workload in ("c3", "c5") and base == wl["base"]:
+                    import bench_strong
+                    ctx._check(ctx.lib.vkt_bcn_cuda_compress(ctx.handle, capi.MODE_BC7, host_src[0].data_ptr(), dims[0][0], dims[0][1], 4, 1,
+                                                             C.byref(params), out_ptrs))
+                    rep = bench_strong.reference_sample(args.workload, bench_strong.STRONG[args.workload], host_src[0].numpy(),
+                                                        [o.numpy() for o in host_out], dims, len(os.sched_getaffinity(0)))
+                    line["parity"] = {k: rep[k] for k in ("against", "blocks", "mismatched_blocks", "bit_exact", "sample")}
+                    line["cpu_baseline"] = {**rep["cpu_blocks_only"], "kind": "reference" if rep["against"].startswith("unmodified") else "port",
+                                            "sample": rep["cpu_blocks_only"]["what"] + " (the blocks of the parity sample; vierkant::bcn::compress() takes no parameters)"}
+            except Exception as e:  # noqa: BLE001
+                line["parity"] = {"error": repr(e)}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
