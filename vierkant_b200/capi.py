@@ -83,7 +83,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.CUDA_SO
+    path = path or os.environ.get("VKT_BCN_LIB") or _build.CUDA_SO  # (VKT_BCN_LIB: a tuning build of the same ABI)
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                                 "(the encoder has no CPU fallback)")
