@@ -1297,6 +1297,14 @@ VKT_FN uint32_t estimate_texel(const Bc7KernelParams &P, const Texel t, uint32_t
     return e;
 }
 
+// (tuning: unroll factors of the two warp-uniform texel-pair loops; 1 = rolled, the shipped setting -- see DESIGN.md 5.0)
+#ifndef VKT_EST_UNROLL_BBOX
+#define VKT_EST_UNROLL_BBOX 1
+#endif
+#ifndef VKT_EST_UNROLL_ERR
+#define VKT_EST_UNROLL_ERR 1
+#endif
+constexpr int kEstUnrollBbox = VKT_EST_UNROLL_BBOX, kEstUnrollErr = VKT_EST_UNROLL_ERR;
 // UNI: `part` is warp-uniform (lists from __constant__ memory, uniform loop control); otherwise lane-varying (shared memory).
 template<bool M7, bool PERC, int KV, bool UNI, int STRIDE>
 VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane<STRIDE> L, uint32_t part, uint64_t best_so_far)
@@ -1344,7 +1352,7 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
                 v0 = n0v, v1 = n1v;
             }
 #else
-#pragma unroll 1
+#pragma unroll kEstUnrollBbox
             for(uint32_t q = q0; q < q1; ++q)
             {
                 const EstPair w = trips[q];
@@ -1390,7 +1398,7 @@ VKT_FN uint64_t estimate_pair(const Bc7Tables &T, const Bc7KernelParams &P, Lane
             uint32_t sum = 0;// every term < 2^28 (host-checked), at most 16 terms
             if(UNI)
             {
-#pragma unroll 1
+#pragma unroll kEstUnrollErr
                 for(uint32_t q = q0; q < q1; ++q)
                 {
                     const EstPair w = trips[q];
