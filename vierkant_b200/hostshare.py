@@ -18,11 +18,21 @@ import time
 import numpy as np
 
 
-def _shm_dir() -> str:
-    for d in ("/dev/shm", os.environ.get("TMPDIR", "/tmp")):
-        if os.path.isdir(d) and os.access(d, os.W_OK):
-            return d
-    return "/tmp"
+def _candidate_dirs() -> list[str]:
+    return [d for d in ("/dev/shm", os.environ.get("TMPDIR", "/tmp"), "/tmp") if os.path.isdir(d) and os.access(d, os.W_OK)]
+
+
+def _dir_with_room(nbytes: int) -> str:
+    """First candidate directory whose file system can hold `nbytes` more (a tmpfs that is too small would only fail later,
+    with SIGBUS on the first touch of a page it cannot back)."""
+    for d in _candidate_dirs():
+        try:
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize >= nbytes + (64 << 20):
+                return d
+        except OSError:
+            continue
+    raise OSError(f"no shared-memory directory with {nbytes >> 20} MB free ({_candidate_dirs()})")
 
 
 class SharedBuffer:
@@ -30,9 +40,15 @@ class SharedBuffer:
     attach after the job's start-up barrier.  `array` is a uint8 numpy view; the creator unlinks the name on close()."""
 
     def __init__(self, name: str, nbytes: int, create: bool):
-        self.path = os.path.join(_shm_dir(), name)
         self.nbytes = int(nbytes)
         self.owner = create
+        if create:
+            self.path = os.path.join(_dir_with_room(self.nbytes), name)
+        else:  # wherever the creator found room
+            found = [os.path.join(d, name) for d in _candidate_dirs() if os.path.exists(os.path.join(d, name))]
+            if not found:
+                raise FileNotFoundError(f"shared buffer {name} not found in {_candidate_dirs()}")
+            self.path = found[0]
         flags = os.O_RDWR | (os.O_CREAT | os.O_TRUNC if create else 0)
         fd = os.open(self.path, flags, 0o600)
         try:
