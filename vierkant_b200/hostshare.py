@@ -43,6 +43,11 @@ class SharedBuffer:
         self.nbytes = int(nbytes)
         self.owner = create
         if create:
+            for d in _candidate_dirs():  # a leftover of a killed run must not be what the other workers find
+                try:
+                    os.unlink(os.path.join(d, name))
+                except OSError:
+                    pass
             self.path = os.path.join(_dir_with_room(self.nbytes), name)
         else:  # wherever the creator found room
             found = [os.path.join(d, name) for d in _candidate_dirs() if os.path.exists(os.path.join(d, name))]
