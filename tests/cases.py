@@ -109,3 +109,34 @@ def tiles_to_image(tiles: np.ndarray, blocks_x: int) -> np.ndarray:
     assert n % blocks_x == 0
     by = n // blocks_x
     return np.ascontiguousarray(tiles.reshape(by, blocks_x, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(by * 4, blocks_x * 4, 4))
+
+
+def random_params(rng):
+    """A random valid parameter set over every knob of bc7enc_compress_block_params (the RDO-only ones included)."""
+    kw = {}
+    opaque = [m for m in (1, 6) if rng.random() < 0.8] or [6]
+    alpha = [m for m in (5, 6, 7) if rng.random() < 0.7] or [6]
+    kw["mode_mask"] = int(sum(1 << m for m in set(opaque) | set(alpha)))
+    kw["max_partitions"] = int(rng.choice([0, 1, 7, 16, 33, 35, 48, 64]))
+    kw["uber_level"] = int(rng.choice([0, 0, 1, 2, 3, 4]))
+    kw["perceptual"] = int(rng.random() < 0.6)
+    if kw["perceptual"]:
+        kw["weights"] = [int(x) for x in rng.integers(1, 200, 4)]
+    else:
+        kw["weights"] = [int(x) for x in rng.integers(1, 40, 4)] if rng.random() < 0.8 else [int(x) for x in rng.integers(1000, 9000, 4)]
+    kw["try_least_squares"] = int(rng.random() < 0.8)
+    kw["mode17_partition_estimation_filterbank"] = int(rng.random() < 0.5)
+    kw["force_alpha"] = int(rng.random() < 0.15)
+    kw["bias_mode1_pbits"] = int(rng.random() < 0.2)
+    kw["pbit1_weight"] = float(rng.choice([1.0, 1.0, 0.7, 1.3, 2.0]))
+    for k in ("mode1_error_weight", "mode5_error_weight", "mode6_error_weight", "mode7_error_weight"):
+        kw[k] = float(rng.choice([1.0, 1.0, 0.8, 1.25]))
+    if rng.random() < 0.25:
+        kw["low_frequency_partition_weight"] = float(rng.choice([0.0, 0.5, 0.75, 1.5]))
+    if rng.random() < 0.2:
+        kw["quant_mode6_endpoints"] = 1
+    if rng.random() < 0.15:
+        kw["force_selectors"] = 1
+        top = 3 if any(m in (5, 7) for m in alpha) else (7 if 1 in opaque else 15)
+        kw["selectors"] = [int(x) for x in rng.integers(0, top + 1, 16)]
+    return kw

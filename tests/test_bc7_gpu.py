@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles, tiles_to_image
+from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles, random_params, tiles_to_image
 from oracle.pyoracle import default_params as oracle_params
 from vierkant_b200 import capi, synth
 
@@ -210,3 +210,20 @@ def test_concurrent_calls_on_one_context(ctx, port_oracle):
         t.join()
     assert not errors
     assert np.array_equal(want_blocks[1], port_oracle.encode_blocks(synth.to_blocks(imgs[1])))
+
+
+def test_random_parameter_sets_match_the_reference(ctx, ref_oracle):
+    """Fuzz over the whole parameter space: 96 random (valid) parameter sets, each on edge-case tiles plus a slice of the alpha
+    texture, GPU against bc7enc_compress_block of the unmodified reference -- every knob in combination, not one at a time."""
+    rng = np.random.default_rng(2026)
+    tex = synth.to_blocks(synth.make_texture(128, 128, 1, seed=7))
+    for case in range(96):
+        kw = random_params(rng)
+        tiles = np.ascontiguousarray(np.concatenate([edge_tiles(1000 + case, 24), tex[(case * 64) % 1000:(case * 64) % 1000 + 160]]))
+        n = tiles.shape[0]
+        pad = (-n) % 16
+        t = np.concatenate([tiles, np.repeat(tiles[-1:], pad, axis=0)]) if pad else tiles
+        got = ctx.encode_bc7(tiles_to_image(t, 16), gpu_params(kw))[:n]
+        want = ref_oracle.encode_blocks(tiles, oracle_params(**kw), threads=os.cpu_count() or 1)
+        bad = int((got != want).any(axis=1).sum())
+        assert bad == 0, f"case {case}: {bad} of {n} blocks differ with {kw}"

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles
+from cases import INVALID_CASES, PARAM_CASES, RDO_CASES, edge_tiles, random_params
 from oracle.pyoracle import Bc7Params, default_params
 from vierkant_b200 import synth
 
@@ -120,3 +120,18 @@ def test_bc5_host_build_matches_the_oracle(emul, port_oracle):
     emul.lib.emul_bc5_encode_blocks.restype = None
     emul.lib.emul_bc5_encode_blocks(tiles.ctypes.data, tiles.shape[0], out.ctypes.data)
     assert np.array_equal(out, port_oracle.encode_bc5_blocks(tiles))
+
+
+def test_random_parameter_sets_host_build_matches_the_port(emul, port_oracle):
+    """The parameter fuzz of tests/test_bc7_gpu.py on the host build of the device code (no GPU needed): 32 random valid
+    parameter sets, every knob in combination, against the oracle."""
+    rng = np.random.default_rng(2026)
+    for case in range(32):
+        kw = random_params(rng)
+        tiles = edge_tiles(1000 + case, 10)
+        p = default_params(**kw)
+        rc, got = emul(tiles, p)
+        assert rc == 0, kw
+        want = port_oracle.encode_blocks(tiles, p, threads=os.cpu_count() or 1)
+        bad = int((got != want).any(axis=1).sum())
+        assert bad == 0, f"case {case}: {bad} of {len(tiles)} blocks differ with {kw}"
