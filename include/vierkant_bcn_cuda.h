@@ -51,7 +51,7 @@ typedef struct vkt_bcn_ctx vkt_bcn_ctx;
  * (only driven by bc7enc_rdo's RDO post-processor, which vierkant does not compile, src/CMakeLists.txt:11) run on a
  * separate, slower kernel variant that keeps the estimator's early-outs (bc7enc.cpp:1536,1810), which such a weight makes
  * observable.  VKT_BCN_ERR_INVALID: uber_level > 4; a mode_mask without an opaque (6 | 1) or an alpha (5 | 6 | 7) mode (the
- * reference asserts); with force_selectors, a selector that does not exist in the palette of every enabled mode (16 / 8 / 4
+ * reference asserts), or with mode 1 as the only opaque mode and max_partitions == 0 (the reference then encodes an uninitialised result); with force_selectors, a selector that does not exist in the palette of every enabled mode (16 / 8 / 4
  * entries for mode 6 / 1 / 5 and 7 -- the reference would read an uninitialised colour); a low-frequency weight that is
  * negative, above 65536 or NaN (the reference's float -> uint64 conversion is undefined there). */
 typedef struct vkt_bc7_params

@@ -55,6 +55,8 @@ INVALID_CASES = {
     "nan_low_freq_weight": dict(low_frequency_partition_weight=float("nan")),
     "uber_level_5": dict(uber_level=5),
     "no_opaque_mode": dict(mode_mask=1 << 5),
+    # mode 1 is the only opaque mode but has no partition to try: the reference encodes an uninitialised result (bc7enc.cpp:2336)
+    "mode1_without_partitions": dict(mode_mask=(1 << 1) | (1 << 5) | (1 << 7), max_partitions=0),
 }
 
 
@@ -118,6 +120,8 @@ def random_params(rng):
     alpha = [m for m in (5, 6, 7) if rng.random() < 0.7] or [6]
     kw["mode_mask"] = int(sum(1 << m for m in set(opaque) | set(alpha)))
     kw["max_partitions"] = int(rng.choice([0, 1, 7, 16, 33, 35, 48, 64]))
+    if 6 not in opaque and kw["max_partitions"] == 0:
+        kw["max_partitions"] = 1  # (mode 1 alone with no partitions is undefined in the reference and refused by the C ABI)
     kw["uber_level"] = int(rng.choice([0, 0, 1, 2, 3, 4]))
     kw["perceptual"] = int(rng.random() < 0.6)
     if kw["perceptual"]:

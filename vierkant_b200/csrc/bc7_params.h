@@ -55,7 +55,10 @@ inline int bc7_prepare_params(const vkt_bc7_params *p, Bc7KernelParams *k)
     if(!(p->low_frequency_partition_weight >= 0.0f && p->low_frequency_partition_weight <= 65536.0f)) { return VKT_BCN_ERR_INVALID; }
     k->ext = (k->force_selectors || k->quant_mode6 || p->low_frequency_partition_weight != 1.0f) ? 1u : 0u;
     const bool alpha_modes = (p->mode_mask & ((1u << 5) | (1u << 6) | (1u << 7))) != 0;
-    const bool opaque_modes = (p->mode_mask & ((1u << 6) | (1u << 1))) != 0;
+    // an opaque block needs mode 6, or mode 1 WITH partitions to try: with mode 6 masked out and max_partitions == 0 the reference
+    // skips mode 1 as well (bc7enc.cpp:2336) and encodes an uninitialised result -- undefined there, refused here (found by the
+    // parameter fuzz of tests/test_bc7_gpu.py)
+    const bool opaque_modes = (p->mode_mask & (1u << 6)) != 0 || ((p->mode_mask & (1u << 1)) != 0 && p->max_partitions > 0);
     if(!alpha_modes || !opaque_modes) { return VKT_BCN_ERR_INVALID; }// the reference asserts (bc7enc.cpp:2141,2295)
     k->mode_mask = p->mode_mask;
     k->max_partitions = p->max_partitions;
