@@ -26,12 +26,15 @@ with capi.BcnContext([0]) as ctx:
     ctx.compress_alloc(b, capi.MODE_BC7, True)
     if os.environ.get("VKT_SAN_BIG"):
         ctx.compress_alloc(synth.make_texture(2048, 1024, 0), capi.MODE_BC7, True)
-    import threading
-    ts = [threading.Thread(target=lambda im=im: ctx.compress(im, capi.MODE_BC7, True)) for im in (a, b, a, b)]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
+    # concurrent calls on lanes: memcheck only (racecheck loses track of launches that several host threads issue at once --
+    # "Internal Sanitizer Error: Detected a failure to track a kernel launch" -- and reports that as a hazard)
+    if not os.environ.get("VKT_SAN_NO_THREADS"):
+        import threading
+        ts = [threading.Thread(target=lambda im=im: ctx.compress(im, capi.MODE_BC7, True)) for im in (a, b, a, b)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
     import ctypes as C
     import numpy as np
     plan = capi.compress_plan(256, 128, True)

@@ -1489,12 +1489,17 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
         if(regroup && it == kKeyIters)
         {
             running = running && (best_err > 0);
-            // Sorted within each class of thread index mod 8, and handed to a thread of the same class: lane columns are
-            // 16 bytes apart, so a quarter warp still covers all eight 16-byte bank groups and the 128-bit loads of the
-            // adopted columns stay conflict-free.  Class r's 32 blocks go, in key order, to lanes r, r+8, r+16, r+24 of
-            // warps 0, 1, ... 7.
+            // One counting sort over the CTA's blocks: warp w adopts blocks [32 w, 32 w + 32) of the key order.  (Round 1 sorted
+            // within each class of thread index mod 8 and handed a block to a thread of its class, so that the 128-bit loads of
+            // the adopted columns kept their conflict-free bank pattern -- at the price of warps that mix eight key windows.
+            // Measured in round 2: the purer warps are worth more than the extra shared-memory wavefronts, 2.000 -> 1.984 ms;
+            // VKT_REGROUP_BY_CLASS restores the old placement.)
             const uint32_t bin = running ? best_it : 15u;// best_it < 14
+#if !defined(VKT_REGROUP_BY_CLASS)
+            const uint32_t cls = 0u;// one sort over the whole CTA (see above)
+#else
             const uint32_t cls = threadIdx.x & 7u;
+#endif
             const uint32_t pos = atomicAdd(&S->cnt[cls][bin], 1u);
             S->err[threadIdx.x] = (uint32_t) best_err;// kNoErr -> 0xFFFFFFFF, above every real error (<= 2^32 - 16)
             S->info[threadIdx.x] = (uint16_t) (best_partition | (running ? 256u : 0u));
@@ -1503,7 +1508,11 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
 #pragma unroll
             for(uint32_t b = 0; b < 15; ++b) { q += (b < bin) ? S->cnt[cls][b] : 0u; }
             constexpr uint32_t kPerWarp = 4;// lanes of one class in a warp
+#if !defined(VKT_REGROUP_BY_CLASS)
+            S->perm[q] = (uint16_t) threadIdx.x;
+#else
             S->perm[(q / kPerWarp) * 32u + (q % kPerWarp) * 8u + cls] = (uint16_t) threadIdx.x;
+#endif
             __syncthreads();
             src = S->perm[threadIdx.x];
             const uint32_t e = S->err[src], info = S->info[src];
@@ -1883,16 +1892,20 @@ VKT_FN uint32_t encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<
     // Second regrouping, by subset size.  The colour-cell searches of mode 1 loop over the texels of a subset, and the lanes
     // of a warp hold partitions with different subset sizes: a raster-order warp runs max(8..15) + max(1..8) = 22 trips where
     // one block needs 16 (20.4 of 32 lanes active in those loops).  Now that every block has its partition, the CTA's blocks
-    // are sorted by the size of their larger subset (8 classes) with the same counting sort as in estimate_partition -- within
-    // each class of thread index mod 8, so the adopted columns stay conflict-free -- and every lane KEEPS the block it
-    // adopts to the end of the kernel: what travels is the column pointer, the partition and the block's identifier (the
+    // are sorted by the size of their larger subset (8 classes) with the same counting sort as in estimate_partition -- over the
+    // whole CTA: pure warps beat the bank pattern here as well, 1.984 -> 1.960 ms, uber 4 2.135 -> 2.08 ms -- and every lane KEEPS
+    // the block it adopts to the end of the kernel: what travels is the column pointer, the partition and the block's identifier (the
     // caller stores the result in that block's slot).  Which lane encodes a block has no influence on the block's result.
     if(!ALPHA && do17 && (STRIDE >= 64) && (STRIDE % 32 == 0))// CTA-uniform
     {
         CtaScratch<STRIDE> *S = reinterpret_cast<CtaScratch<STRIDE> *>(L.p - threadIdx.x + 16 * STRIDE);
         const uint32_t n0 = T.est_n0[part17];
         const uint32_t bin = umax(n0, 16u - n0) - 8u;// 0..7
+#if !defined(VKT_REGROUP_BY_CLASS)
+        const uint32_t cls = 0u;
+#else
         const uint32_t cls = threadIdx.x & 7u;
+#endif
         const uint32_t pos = atomicAdd(&S->cnt2[cls][bin], 1u);
         S->err[threadIdx.x] = gid;
         S->info[threadIdx.x] = (uint16_t) part17;
@@ -1900,7 +1913,11 @@ VKT_FN uint32_t encode_block(const Bc7Tables &T, const Bc7KernelParams &P, Lane<
         uint32_t q = pos;
 #pragma unroll
         for(uint32_t b = 0; b < 7; ++b) { q += (b < bin) ? S->cnt2[cls][b] : 0u; }
+#if !defined(VKT_REGROUP_BY_CLASS)
+        S->perm[q] = (uint16_t) threadIdx.x;
+#else
         S->perm[(q / 4u) * 32u + (q % 4u) * 8u + cls] = (uint16_t) threadIdx.x;
+#endif
         __syncthreads();
         const uint32_t src = S->perm[threadIdx.x];
         gid = S->err[src];
