@@ -1474,7 +1474,12 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
     // time (the three barriers eat most of the 13 % fewer candidates); keeping the adopted blocks for the rest of the
     // kernel instead of sending results back was slower.
     // (opaque kernels only: on the alpha kernels, 2 CTAs per SM, the barriers cost more than the smaller union saves)
-    const bool regroup = !M7 && KEY28 && (STRIDE >= 64) && (STRIDE % 32 == 0) && P.filterbank && (uniform_end > kKeyIters);// CTA-uniform
+#if defined(VKT_EST_REGROUP_ALPHA)
+    constexpr bool kRegroupM7 = true;
+#else
+    constexpr bool kRegroupM7 = false;
+#endif
+    const bool regroup = (!M7 || kRegroupM7) && KEY28 && (STRIDE >= 64) && (STRIDE % 32 == 0) && P.filterbank && (uniform_end > kKeyIters);// CTA-uniform
     CtaScratch<STRIDE> *S = reinterpret_cast<CtaScratch<STRIDE> *>(L.p - threadIdx.x + 16 * STRIDE);
     uint32_t src = threadIdx.x;
     bool adopted = false;
