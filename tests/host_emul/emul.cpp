@@ -105,6 +105,40 @@ int emul_resize_decode_mismatches()
     return bad;
 }
 
+// the fused pass's two-instruction decode (resize_decode_split) against v / 255.0f, and its float(v) from the 2^23 + v bit pattern
+int emul_resize_decode_split_mismatches()
+{
+    int bad = 0;
+    for(uint32_t v = 0; v < 256; ++v)
+    {
+        volatile float want = (float) v / 255.0f;
+        const uint32_t bits = 0x4B000000u | v;
+        float m;
+        std::memcpy(&m, &bits, sizeof(m));
+        volatile float fv = m - 8388608.0f;
+        bad += (fv != (float) v) || (vkt::resize_decode_split(fv) != want);
+    }
+    return bad;
+}
+
+// the conversion-free encode (resize_encode_u8) against (int)((double) s + 0.5) for every `stride`-th float in [0, 255]
+// (stride 1: all 1.13e9 of them, a few seconds)
+long long emul_resize_encode_mismatches(uint32_t stride)
+{
+    long long bad = 0;
+    const float top = 255.0f;
+    uint32_t hi;
+    std::memcpy(&hi, &top, sizeof(hi));
+    for(uint64_t b = 0; b <= hi; b += stride ? stride : 1)
+    {
+        const uint32_t bits = (uint32_t) b;
+        float s;
+        std::memcpy(&s, &bits, sizeof(s));
+        bad += vkt::resize_encode_u8(s) != (uint32_t) (int) ((double) s + 0.5);
+    }
+    return bad;
+}
+
 // BC4 selector count: the reciprocal multiplication of bc5_core.cuh against the seven threshold compares of rgbcx
 // (rgbcx.cpp:2655-2683), for every delta and every reachable numerator.  Returns the number of disagreements.
 int emul_bc4_count_mismatches()

@@ -47,6 +47,64 @@ def test_resize_large_is_banded_and_exact(ctx, port_oracle):
     assert np.array_equal(ctx.resize_u8(img, 2048, 1024), port_oracle.resize(img, 2048, 1024))
 
 
+# Regular axes (1:1 and 2:1) with >= 2^16 output samples take the strip kernels (resize_strip_kernel<1,3,4> / <2,8,2>): widths that
+# are no multiple of a CTA's columns, heights that are no multiple of the strip or of its unrolled period, the shorter strips of
+# calls with few threads.
+STRIP_SHAPES = [(4096, 1024, 4096, 1024), (4096, 1024, 2048, 512), (520, 2020, 520, 2020), (1048, 4004, 524, 2002), (16384, 68, 16384, 68),
+                (32768, 136, 16384, 68), (256, 256, 256, 256), (512, 512, 256, 256), (1024, 100, 1024, 100), (2048, 202, 1024, 101)]
+
+
+def _strip_images(w, h):
+    rng = np.random.default_rng(7 * w + h)
+    noise = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    # extreme samples next to each other (saturation, the -0 / +0 paths of the encode), then flat 0 / 255 bands
+    hard = np.where(rng.random((h, w, 4)) < 0.5, 0, 255).astype(np.uint8)
+    hard[: h // 4] = 0
+    hard[h // 4: h // 2] = 255
+    return noise, hard
+
+
+@pytest.mark.parametrize("w,h,ow,oh", STRIP_SHAPES)
+def test_resize_strip_kernels_match_oracle(ctx, port_oracle, w, h, ow, oh):
+    for img in _strip_images(w, h):
+        want = port_oracle.resize(img, ow, oh)
+        got = ctx.resize_u8(img, ow, oh)
+        assert np.array_equal(got, want), int((got != want).sum())
+
+
+_NARROW = """
+import sys
+import numpy as np
+sys.path[:0] = [{root!r}, {tests!r}]
+from oracle import pyoracle
+from vierkant_b200 import capi
+port = pyoracle.PortOracle()
+shapes = [(4, 4, 4, 4), (8, 8, 4, 4), (4, 64, 4, 64), (8, 128, 4, 64), (8, 6, 8, 6), (16, 10, 8, 5), (516, 20, 516, 20), (1032, 40, 516, 20),
+          (260, 12, 260, 12), (12, 300, 12, 300), (24, 600, 12, 300), (64, 37, 64, 37), (128, 74, 64, 37), (512, 3, 512, 3), (1028, 2, 514, 1)]
+with capi.BcnContext([0]) as ctx:
+    for w, h, ow, oh in shapes:
+        rng = np.random.default_rng(w * 31 + h)
+        for img in (rng.integers(0, 256, (h, w, 4), dtype=np.uint8), np.where(rng.random((h, w, 4)) < 0.5, 0, 255).astype(np.uint8)):
+            got, want = ctx.resize_u8(img, ow, oh), port.resize(img, ow, oh)
+            assert np.array_equal(got, want), (w, h, ow, oh, int((got != want).sum()))
+    launches = ctx.stats()["kernel_launches"]
+assert launches == 2 * len(shapes), launches  # one strip-kernel launch per call (the general passes take two)
+print("narrow ok")
+"""
+
+
+def test_resize_strip_kernels_narrow_shapes():
+    """The strip kernels' column-group edge cases -- one thread per row (first == last), two threads, a partial warp -- need
+    images far below the size at which the library picks those kernels: VKT_BCN_STRIP_MIN=1 (read once per process) sends every
+    regular call to them."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _NARROW.format(root=root, tests=os.path.join(root, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "VKT_BCN_STRIP_MIN": "1"}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "narrow ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_bc5_matches_golden_and_oracle(ctx, port_oracle):
     golden = np.load(os.path.join(GOLD, "bc7_blocks.npz"))
     tiles = golden["tiles"]

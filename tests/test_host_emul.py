@@ -80,6 +80,17 @@ def test_resize_decode_is_the_exact_quotient(emul):
     assert emul.lib.emul_resize_decode_mismatches() == 0
 
 
+def test_resize_strip_kernel_arithmetic_is_exact(emul):
+    """The strip kernels' conversion-free sample arithmetic: float(v) from the 2^23 + v bit pattern and the two-instruction
+    quotient for all 256 values; the two round-toward-zero additions of the encode against (int)((double) s + 0.5) for
+    EVERY float in [0, 255] (1.13e9 values)."""
+    import ctypes as C
+    assert emul.lib.emul_resize_decode_split_mismatches() == 0
+    emul.lib.emul_resize_encode_mismatches.restype = C.c_longlong
+    emul.lib.emul_resize_encode_mismatches.argtypes = [C.c_uint32]
+    assert emul.lib.emul_resize_encode_mismatches(1) == 0
+
+
 def test_resize_tap_lists_ascend(emul):
     """The vertical CUDA pass visits input rows in ascending order and feeds each to the outputs whose next tap it is: every
     tap list must ascend (repeats allowed: clamped margins), for reductions, enlargements and the 1:1 Mitchell pass."""

@@ -537,12 +537,15 @@ static int launch_bc7_batch(vkt_bcn_ctx *ctx, DeviceSlot *s, const DevImage *ima
             VKT_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void **>(&scratch), 256 + 2 * list_bytes, stream));
             uint32_t *counts = reinterpret_cast<uint32_t *>(scratch);
             uint32_t *list_o = reinterpret_cast<uint32_t *>(scratch + 256), *list_a = reinterpret_cast<uint32_t *>(scratch + 256 + list_bytes);
-            VKT_CUDA(ctx, cudaMemsetAsync(counts, 0, 8, stream));
-            bc7_classify_kernel<<<(B.total_blocks + 255) / 256, 256, 0, stream>>>(B, counts, list_o, list_a);
-            encode(false, list_o, counts);
-            encode(true, list_a, counts + 1);
-            const cudaError_t e = cudaGetLastError();
-            VKT_CUDA(ctx, cudaFreeAsync(scratch, stream));
+            cudaError_t e = cudaMemsetAsync(counts, 0, 8, stream);
+            if(e == cudaSuccess)
+            {
+                bc7_classify_kernel<<<(B.total_blocks + 255) / 256, 256, 0, stream>>>(B, counts, list_o, list_a);
+                encode(false, list_o, counts);
+                encode(true, list_a, counts + 1);
+                e = cudaGetLastError();
+            }
+            VKT_CUDA(ctx, cudaFreeAsync(scratch, stream));// (also when something above failed: the scratch never leaks)
             VKT_CUDA(ctx, e);
             count(ctx, 3, 0, 0);
         }

@@ -3,6 +3,8 @@
 // Build with -ffp-contract=off: the coefficient arithmetic must round exactly like the reference's x86-64 build.
 #pragma once
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 #include <vector>
 
 namespace vkt
@@ -27,6 +29,41 @@ VKT_RESIZE_HD inline float resize_decode_u8(uint32_t v)
 #else
     const float q0 = fv * r;
     return fmaf(fmaf(-q0, 255.0f, fv), r, q0);
+#endif
+}
+
+// The same quotient from a sample that already is a float (the fused pass builds float(v) with a byte permute and one add):
+// v / 255 = v * hi + v * lo with hi = RN(1/255), lo = RN(1/255 - hi).  fma(v, hi, RN(v * lo)) rounds once, from a value that is
+// exact to ~2^-50 -- correctly rounded for all 256 values (exhaustive: tests/test_host_emul.py); two FMA-pipe instructions.
+VKT_RESIZE_HD inline float resize_decode_split(float fv)
+{
+    const float hi = 1.0f / 255.0f;                                          // 0x3B808081
+    const float lo = (float) (1.0 / 255.0 - (double) (1.0f / 255.0f));// 0xAF7EFEFF
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(fv, hi, __fmul_rn(fv, lo));
+#else
+    return fmaf(fv, hi, fv * lo);
+#endif
+}
+
+// stbir's encode of a saturated sample s = sat(f) * 255.0f in [0, 255] (:1737-1763): (int)((double) s + 0.5), i.e. floor(s + 0.5)
+// of the EXACT sum.  Two additions that round toward zero do the same without a conversion: RZ(s + 0.5) never crosses an
+// integer upwards (integers are representable), so its floor is that of the exact sum, and RZ(. + 2^23) leaves that floor in the
+// low mantissa bits.  Exhaustively equal for every float in [0, 255] (tests/test_host_emul.py).
+VKT_RESIZE_HD inline uint32_t resize_encode_u8(float s)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(__fadd_rz(__fadd_rz(s, 0.5f), 8388608.0f)) & 255u;
+#else
+    auto rz = [](double x) {// x rounded to float toward zero
+        float f = (float) x;
+        if(std::fabs((double) f) > std::fabs(x)) { f = std::nextafterf(f, 0.0f); }
+        return f;
+    };
+    const float u = rz((double) rz((double) s + 0.5) + 8388608.0);
+    uint32_t bits;
+    std::memcpy(&bits, &u, sizeof(bits));
+    return bits & 255u;
 #endif
 }
 
