@@ -107,15 +107,25 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
-    def start(self):
+    def start(self, wait_s: float = 3.0):
+        """Start polling (every 20 ms) and wait until the first sample has arrived: nvidia-smi can take longer to come up
+        than a short timed region lasts.  Call it before the warm-up and mark() right before the timed region."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < wait_s and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples from here on belong to the timed region (earlier ones: warm-up, kept only if the region gets none)."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -132,7 +142,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in (self.lines[self.first:] or self.lines):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -410,13 +420,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- kernel-only ------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # (before the warm-up: the poller is up and sampling when the timed region begins)
     for i in range(args.warmup):
         step_device(i)
     barrier()
     s0 = ctx.stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cur = torch.cuda.current_stream()
     e0.record(cur)  # the device is idle here (barrier above): both lanes start after this point

@@ -617,10 +617,20 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
                 }
             }
             else
+            {
+            // The opaque uber kernels (two CTAs per SM, registers to spare) request the next texel's record before the current one
+            // is searched: uber 4 2.08 -> 2.05 ms per 2048^2 level.  The default opaque kernel gains nothing once its blocks are
+            // regrouped in candidate order (80-register budget), the alpha kernels lose 0.5 % (profiles/r2_ee_binperm_exp.txt).
+#if defined(VKT_EVAL_NO_PREFETCH)
+            constexpr bool PREFETCH = false;
+#else
+            constexpr bool PREFETCH = ROOMY && !ALPHA && (MODE != 5);
+#endif
+            Texel tn = L.at(cell.at(0));
             for(int k = 0; k < cell.n; ++k)
             {
-                const int i = cell.at(k);
-                const Texel t = L.at(i);
+                const Texel t = PREFETCH ? tn : L.at(cell.at(k));
+                if(PREFETCH) { tn = L.at(cell.at((k + 1 < cell.n) ? k + 1 : k)); }
                 const int l2 = t.l, ncr2 = -t.cr, ncb2 = -t.cb;
                 const int a2 = ALPHA ? (int) (t.px >> 24) : 0;
                 uint32_t key = 0xFFFFFFFFu;
@@ -640,6 +650,7 @@ VKT_FN void evaluate(const Bc7KernelParams &P, Lane<STRIDE> L, CellRef cell, uin
                 }
                 total += (uint64_t) (key >> 4);
                 sel |= (uint64_t) (key & 15u) << (4 * k);
+            }
             }
         }
         else
@@ -1499,7 +1510,17 @@ VKT_FN uint32_t estimate_partition(const Bc7Tables &T, const Bc7KernelParams &P,
             // the adopted columns kept their conflict-free bank pattern -- at the price of warps that mix eight key windows.
             // Measured in round 2: the purer warps are worth more than the extra shared-memory wavefronts, 2.000 -> 1.984 ms;
             // VKT_REGROUP_BY_CLASS restores the old placement.)
+            // The sort key is not the key iteration itself but its place in an order that puts keys with similar candidate sets
+            // next to each other: a warp takes 32 consecutive blocks of the sorted CTA, i.e. two or three neighbouring bins, and
+            // pays for the union of their sets.  The order was annealed on the candidate sets of T.pred against the key histograms
+            // of four textures and a uniform one (all within 0.1 of each other): mean union per warp 17.3 -> 15.7 candidates of
+            // the 14.1 a block needs, the slowest warp of a CTA -- which the write-back barrier waits for -- 21.0 -> 18.0.
+#if !defined(VKT_REGROUP_PLAIN_BINS)
+            constexpr uint64_t kBinOfKey = 0xC2178590AD63B4ull;// nibble k: bin of key iteration k = {4,11,3,6,13,10,0,9,5,8,7,1,2,12}
+            const uint32_t bin = running ? ((uint32_t) (kBinOfKey >> (4u * best_it)) & 15u) : 15u;// best_it < 14
+#else
             const uint32_t bin = running ? best_it : 15u;// best_it < 14
+#endif
 #if !defined(VKT_REGROUP_BY_CLASS)
             const uint32_t cls = 0u;// one sort over the whole CTA (see above)
 #else
