@@ -45,7 +45,7 @@ sys.path.insert(0, ROOT)
 from vierkant_b200 import synth  # noqa: E402
 
 BYTES_PER_PIXEL = 5.0          # 64 B in + 16 B out per 16-pixel block
-NCU_TRAFFIC_BYTES = 77.54e6    # measured DRAM bytes of the C2 level-0 launch (ncu --set full, profiles/r2_p_opaque_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = 77.48e6    # measured DRAM bytes of the C2 level-0 launch (ncu --set full, profiles/r2_ff_opaque_ncu_summary.txt)
 
 # BASELINE.json configs.  The default (and the only one the driver runs) is configs[1]; the others are selectable with
 # --workload for the numbers quoted in DESIGN.md.  ops_per_pixel: algorithmic scalar ops (gcov
@@ -608,7 +608,7 @@ def main():
                          "frac": achieved / alu_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch, one `ncu --set full` capture
                          "traffic": NCU_TRAFFIC_BYTES if (args.workload == "c2" and base == wl["base"]) else None,
-                         "traffic_source": "profiles/r2_p_opaque_ncu_summary.txt (73.26 MB read + 4.28 MB written; algorithmic 83.9 MB, part of the writes still in L2)",
+                         "traffic_source": "profiles/r2_ff_opaque_ncu_summary.txt (73.28 MB read + 4.21 MB written; algorithmic 83.9 MB, part of the writes still in L2)",
                          "kernel": f"bc7_encode_kernel<perceptual> launch set on level 0 ({base}x{base})", "kernel_ms": kernel_ms,
                          "ops_per_pixel": OPS_PER_PIXEL, "ops_source": ops_source,
                          "peak_source": f"{props.multi_processor_count} SMs x 4 x 32 lanes x {peaks.get('sm_max_mhz', 1965.0):.0f} MHz ({peak_src} clock)",
