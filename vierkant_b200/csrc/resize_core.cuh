@@ -499,6 +499,7 @@ static int resize_device(vkt_bcn_ctx *ctx, DeviceSlot *s, const uint8_t *d_src, 
         // regular axes (every level of a power-of-two chain): the fused pass, no fp32 band
         const uint32_t rows = out_y1 - out_y0;
         int strip = strip_env > 0 ? strip_env : 16;// measured on 4096^2 chains: 8 / 16 / 32 rows per strip 3.10 / 3.08 / 3.15 ms (general passes: 3.23)
+        while((rows + uint32_t(strip) - 1u) / uint32_t(strip) > 65535u) { strip *= 2; }// (grid.y limit: more than a million output rows)
         if(strip2)
         {
             const int least = (ax->reg_step == 1) ? 4 : 8;
