@@ -14,6 +14,7 @@
 #include "../../vierkant_b200/csrc/bc7_params.h"
 #include "../../vierkant_b200/csrc/chain_plan.h"
 #include "../../vierkant_b200/csrc/resize_axis.h"
+#include "../../vierkant_b200/csrc/resize_strip.h"
 
 // the uber-free instantiation whenever the parameters allow it, as the CUDA dispatch does
 template<bool PERC, int KV, bool ALPHA>
@@ -249,6 +250,47 @@ int emul_bc7_encode_blocks(const uint8_t *px, uint64_t num_blocks, const vkt_bc7
             pool.emplace_back(work, num_blocks * t / threads, num_blocks * (t + 1) / threads);
         }
         for(auto &t: pool) { t.join(); }
+    }
+    return 0;
+}
+
+// The resize strip kernels (resize_strip.h: the body the CUDA kernels run per thread) executed thread by thread on the host:
+// RGBA image w x h -> ow x oh (ow == w, oh == h or w == 2 ow, h == 2 oh), output rows [y0, y1) in strips of `strip` rows, exactly as
+// resize_device launches them (one call per row range).  Rows outside [y0, y1) of `out` are left untouched.
+// Returns 0, or -1 when the axes are not regular / uniform (the product would take another path).
+int emul_resize_strip(const uint8_t *in, uint32_t w, uint32_t h, uint8_t *out, uint32_t ow, uint32_t oh, uint32_t y0, uint32_t y1, int strip)
+{
+    vkt::ResizeAxis ax, ay;
+    ax.build((int) w, (int) ow);
+    ay.build((int) h, (int) oh);
+    const int S = (w == ow) ? 1 : 2, T = (S == 1) ? 3 : 8, NC = (S == 1) ? 4 : 2;
+    if((w != ow && w != 2 * ow) || (h != oh && h != 2 * oh) || (w == ow) != (h == oh) || ow % uint32_t(NC) || w % 4u || strip <= 0 || y1 > oh) { return -1; }
+    vkt::FusedCoef cx = {}, cy = {};
+    for(const vkt::ResizeAxis *a: {&ax, &ay})
+    {
+        const int in_n = a->in_size, out_n = a->out_size;
+        for(int o = 0; o < out_n; ++o)
+        {
+            if(a->start[size_t(o) + 1] - a->start[size_t(o)] != T) { return -1; }
+            for(int t = 0; t < T; ++t)
+            {
+                const int v = S * o - (T - S) / 2 + t, want = v < 0 ? 0 : (v >= in_n ? in_n - 1 : v);
+                if(a->idx[size_t(a->start[size_t(o)] + t)] != want) { return -1; }
+                if(memcmp(&a->coef[size_t(a->start[size_t(o)] + t)], &a->coef[size_t(a->start[0] + t)], sizeof(float)) != 0) { return -1; }
+            }
+        }
+        for(int t = 0; t < T; ++t) { (a == &ax ? cx : cy).c[t] = a->coef[size_t(a->start[0] + t)]; }
+    }
+    const int groups = int(ow) / NC, strips = (int(y1 - y0) + strip - 1) / strip;
+    // (a CTA is 128 threads: run the surplus threads of the last CTA as well -- they must return without touching anything)
+    const int threads = (groups + 127) / 128 * 128;
+    for(int by = 0; by < strips; ++by)
+    {
+        for(int k = 0; k < threads; ++k)
+        {
+            if(S == 1) { vkt::resize_strip_thread<1, 3, 4>(in, int(w), int(h), int(ow), int(y0), int(y1), strip, cx, cy, out, k, by); }
+            else { vkt::resize_strip_thread<2, 8, 2>(in, int(w), int(h), int(ow), int(y0), int(y1), strip, cx, cy, out, k, by); }
+        }
     }
     return 0;
 }

@@ -91,6 +91,33 @@ def test_resize_strip_kernel_arithmetic_is_exact(emul):
     assert emul.lib.emul_resize_encode_mismatches(1) == 0
 
 
+# (w, h, ow, oh, strip, y0, y1) -- y1 == 0: all rows.  One thread per row (first == last), two, a partial warp, more than one CTA
+# of column groups; heights that are no multiple of the strip or of the unrolled period (3 / 4 rows); row ranges as the band loop
+# of compress() issues them; the strips the library picks (16, 8, 4).
+STRIP_CASES = [(4, 4, 4, 4, 16, 0, 0), (8, 8, 4, 4, 8, 0, 0), (4, 64, 4, 64, 4, 0, 0), (8, 128, 4, 64, 16, 0, 0), (8, 6, 8, 6, 4, 0, 0),
+               (16, 10, 8, 5, 8, 0, 0), (516, 20, 516, 20, 16, 0, 0), (1032, 40, 516, 20, 8, 0, 0), (260, 12, 260, 12, 4, 0, 0),
+               (12, 300, 12, 300, 16, 0, 0), (24, 600, 12, 300, 16, 0, 0), (64, 37, 64, 37, 16, 0, 0), (128, 74, 64, 37, 16, 0, 0),
+               (512, 3, 512, 3, 16, 0, 0), (1028, 2, 514, 1, 8, 0, 0), (8, 4, 8, 4, 1, 0, 0), (8, 8, 4, 4, 1, 0, 0),
+               (256, 96, 256, 96, 16, 17, 63), (256, 96, 256, 96, 4, 0, 5), (512, 192, 256, 96, 16, 31, 96), (512, 192, 256, 96, 8, 5, 6),
+               (2048, 24, 2048, 24, 16, 0, 0), (2056, 48, 1028, 24, 16, 0, 0)]
+
+
+@pytest.mark.parametrize("w,h,ow,oh,strip,y0,y1", STRIP_CASES)
+def test_resize_strip_thread_matches_oracle(emul, port_oracle, w, h, ow, oh, strip, y0, y1):
+    """The per-thread body of the CUDA strip kernels (resize_strip.h), run thread by thread on the host -- surplus threads of the
+    last CTA included -- against the oracle: the same bytes inside the requested rows, nothing written outside them."""
+    lib = emul.lib
+    lib.emul_resize_strip.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    y1 = y1 or oh
+    rng = np.random.default_rng(13 * w + h + strip)
+    for img in (rng.integers(0, 256, (h, w, 4), dtype=np.uint8), np.where(rng.random((h, w, 4)) < 0.5, 0, 255).astype(np.uint8)):
+        want = port_oracle.resize(img, ow, oh)
+        out = np.full((oh, ow, 4), 0xAB, dtype=np.uint8)
+        assert lib.emul_resize_strip(img.ctypes.data, w, h, out.ctypes.data, ow, oh, y0, y1, strip) == 0
+        assert np.array_equal(out[y0:y1], want[y0:y1]), int((out[y0:y1] != want[y0:y1]).sum())
+        assert (out[:y0] == 0xAB).all() and (out[y1:] == 0xAB).all()
+
+
 def test_resize_tap_lists_ascend(emul):
     """The vertical CUDA pass visits input rows in ascending order and feeds each to the outputs whose next tap it is: every
     tap list must ascend (repeats allowed: clamped margins), for reductions, enlargements and the 1:1 Mitchell pass."""

@@ -23,6 +23,7 @@
 
 #include "chain_plan.h"
 #include "resize_axis.h"
+#include "resize_strip.h"
 
 namespace vkt
 {
@@ -234,147 +235,12 @@ __global__ void __launch_bounds__(128) resize_fused_kernel(const uint8_t *__rest
 }
 
 
-// ---- strip kernel, second version (round 2): the same sums with a third of the instructions.
-// What the first version spends per output sample at 2:1 is 643 instructions, 256 of them decoding (every source sample is decoded
-// by the four threads whose taps reach it, each time I2F.U8 on the conversion unit + 3 FMA-pipe instructions) and 29 + 12 encoding
-// four channels (F2I, I2F, compare, two adds; compare, min, select to saturate).  Here
-//   * a thread owns NC adjacent output columns (4 at 1:1, 2 at 2:1): the source samples its taps share are loaded (128-bit) and
-//     decoded once -- 1.5 (1:1) / 5 (2:1) samples per output column and input row instead of 3 / 8;
-//   * float(v) is the bit pattern 0x4B000000 | v (= 2^23 + v, one PRMT straight from the packed pixel) minus 2^23, and
-//     v / 255.0f two more FMA-pipe instructions (resize_decode_split): no conversion-unit instruction;
-//   * the coefficients of a regular axis are the same for every output (DeviceAxis::reg_uniform): kernel parameters, i.e. constant
-//     bank operands -- no tap tables, no registers;
-//   * the register window of filtered rows is indexed modulo T at compile time (the row loop is unrolled over one period), so
-//     nothing is moved between registers;
-//   * saturation rides on the last vertical addition (add.sat), and the encode is resize_encode_u8: two round-toward-zero
-//     additions and a byte permute, no conversion.
-// Sums, operand order and roundings are those of resize_h_kernel / resize_v_kernel; the only liberty is that a sum starts with
-// its first product instead of 0.0f + product, which can turn a +0 into a -0 and nothing else -- the encoded byte is 0 either way.
-struct FusedCoef
-{
-    float c[8];
-};
-
-template<int CH>
-__device__ __forceinline__ float resize_byte_as_float(uint32_t q)
-{
-    return __fadd_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440u + CH)), -8388608.0f);
-}
-
-__device__ __forceinline__ float resize_fadd_sat(float a, float b)
-{
-    float d;
-    asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-
+// ---- strip kernel, second version (round 2): the per-thread body lives in resize_strip.h (host and device).
 template<int S, int T, int NC>
 __global__ void __launch_bounds__(128) resize_strip_kernel(const uint8_t *__restrict__ src, int in_w, int in_h, int out_w, int y0, int y1, int strip,
                                                             const FusedCoef cx, const FusedCoef cy, uint8_t *__restrict__ dst)
 {
-    static_assert((S == 1 && T == 3 && NC == 4) || (S == 2 && T == 8 && NC == 2), "1:1 Mitchell (3 taps) or 2:1 Mitchell (8 taps)");
-    constexpr int OFF = -(T - S) / 2;           // first tap of output o is sample S * o + OFF: -1 / -3
-    constexpr int NP = S * (NC - 1) + T;        // source samples per input row and thread: 6 / 10
-    constexpr int P = (S == 1) ? T : T / S;     // output rows after which the window slots repeat: 3 / 4
-    const int k = blockIdx.x * 128 + int(threadIdx.x);
-    const int x = k * NC;
-    const int ya = y0 + int(blockIdx.y) * strip, yb = min(ya + strip, y1);
-    if(x >= out_w || ya >= yb) { return; }
-    const bool first = (k == 0), last = (x + NC >= out_w);// (out_w is a multiple of NC: checked by the caller)
-
-    // horizontally filtered samples of (virtual) input row v at this thread's NC columns
-    auto hrow = [&](int v, float4 (&h)[NC]) {
-        const int r = v < 0 ? 0 : (v >= in_h ? in_h - 1 : v);
-        const uint32_t *row = reinterpret_cast<const uint32_t *>(src) + size_t(r) * size_t(in_w);
-        uint32_t px[NP];// samples S * x + OFF + i, clamped to the row
-        if(S == 1)
-        {
-            // 4k-1 | 4k .. 4k+3 | 4k+4
-            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(row + x));
-            px[0] = __ldg(row + (first ? 0 : x - 1));
-            px[1] = m.x, px[2] = m.y, px[3] = m.z, px[4] = m.w;
-            px[NP - 1] = __ldg(row + (last ? in_w - 1 : x + 4));
-        }
-        else
-        {
-            // 4k-3 .. 4k+6 out of the three aligned groups 4k-4.., 4k.., 4k+4.. (edge threads repeat the edge sample)
-            const int g = 2 * x;// 4k
-            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(row + g));
-            uint4 a = b, c = b;
-            if(!first) { a = __ldg(reinterpret_cast<const uint4 *>(row + g - 4)); }
-            else { a.y = a.z = a.w = b.x; }
-            if(!last) { c = __ldg(reinterpret_cast<const uint4 *>(row + g + 4)); }
-            else { c.x = c.y = c.z = b.w; }
-            px[0] = a.y, px[1] = a.z, px[2] = a.w, px[3] = b.x, px[4] = b.y, px[5] = b.z, px[6] = b.w;
-            px[7] = c.x, px[8] = c.y, px[NP - 1] = c.z;
-        }
-#pragma unroll
-        for(int i = 0; i < NP; ++i)
-        {
-            const float d0 = resize_decode_split(resize_byte_as_float<0>(px[i])), d1 = resize_decode_split(resize_byte_as_float<1>(px[i]));
-            const float d2 = resize_decode_split(resize_byte_as_float<2>(px[i])), d3 = resize_decode_split(resize_byte_as_float<3>(px[i]));
-#pragma unroll
-            for(int j = 0; j < NC; ++j)
-            {
-                const int t = i - S * j;// sample i is tap t of column j (taps ascend with i: the reference's order)
-                if(t == 0)
-                {
-                    h[j].x = __fmul_rn(d0, cx.c[0]), h[j].y = __fmul_rn(d1, cx.c[0]);
-                    h[j].z = __fmul_rn(d2, cx.c[0]), h[j].w = __fmul_rn(d3, cx.c[0]);
-                }
-                else if(t > 0 && t < T)
-                {
-                    h[j].x = __fadd_rn(h[j].x, __fmul_rn(d0, cx.c[t])), h[j].y = __fadd_rn(h[j].y, __fmul_rn(d1, cx.c[t]));
-                    h[j].z = __fadd_rn(h[j].z, __fmul_rn(d2, cx.c[t])), h[j].w = __fadd_rn(h[j].w, __fmul_rn(d3, cx.c[t]));
-                }
-            }
-        }
-    };
-
-    // win[(S * m + t) % T] = filtered virtual row S * (ya + m) + OFF + t, the t-th tap of output row ya + m
-    float4 win[T][NC];
-    const int base = S * ya + OFF;
-#pragma unroll
-    for(int t = 0; t < T - S; ++t) { hrow(base + t, win[t]); }
-    uint32_t *out = reinterpret_cast<uint32_t *>(dst) + size_t(ya) * size_t(out_w) + size_t(x);
-#pragma unroll 1
-    for(int m0 = 0; ya + m0 < yb; m0 += P)
-    {
-#pragma unroll
-        for(int u = 0; u < P; ++u)
-        {
-            if(ya + m0 + u >= yb) { break; }
-#pragma unroll
-            for(int t = T - S; t < T; ++t) { hrow(base + S * (m0 + u) + t, win[(S * u + t) % T]); }
-            uint32_t q[NC];
-#pragma unroll
-            for(int j = 0; j < NC; ++j)
-            {
-                const float4 w0 = win[(S * u) % T][j];
-                float a0 = __fmul_rn(w0.x, cy.c[0]), a1 = __fmul_rn(w0.y, cy.c[0]), a2 = __fmul_rn(w0.z, cy.c[0]), a3 = __fmul_rn(w0.w, cy.c[0]);
-#pragma unroll
-                for(int t = 1; t < T - 1; ++t)
-                {
-                    const float4 w = win[(S * u + t) % T][j];
-                    a0 = __fadd_rn(a0, __fmul_rn(w.x, cy.c[t])), a1 = __fadd_rn(a1, __fmul_rn(w.y, cy.c[t]));
-                    a2 = __fadd_rn(a2, __fmul_rn(w.z, cy.c[t])), a3 = __fadd_rn(a3, __fmul_rn(w.w, cy.c[t]));
-                }
-                const float4 wl = win[(S * u + T - 1) % T][j];
-                // stbir__saturate (:572-581) on the last addition, then (int)(f * 255.0f + 0.5)
-                a0 = resize_fadd_sat(a0, __fmul_rn(wl.x, cy.c[T - 1])), a1 = resize_fadd_sat(a1, __fmul_rn(wl.y, cy.c[T - 1]));
-                a2 = resize_fadd_sat(a2, __fmul_rn(wl.z, cy.c[T - 1])), a3 = resize_fadd_sat(a3, __fmul_rn(wl.w, cy.c[T - 1]));
-                const uint32_t e0 = __float_as_uint(__fadd_rz(__fadd_rz(__fmul_rn(a0, 255.0f), 0.5f), 8388608.0f));
-                const uint32_t e1 = __float_as_uint(__fadd_rz(__fadd_rz(__fmul_rn(a1, 255.0f), 0.5f), 8388608.0f));
-                const uint32_t e2 = __float_as_uint(__fadd_rz(__fadd_rz(__fmul_rn(a2, 255.0f), 0.5f), 8388608.0f));
-                const uint32_t e3 = __float_as_uint(__fadd_rz(__fadd_rz(__fmul_rn(a3, 255.0f), 0.5f), 8388608.0f));
-                // (resize_encode_u8 four times; the bytes sit in the low mantissa bits)
-                q[j] = __byte_perm(__byte_perm(e0, e1, 0x0040u), __byte_perm(e2, e3, 0x0040u), 0x5410u);
-            }
-            if(NC == 4) { *reinterpret_cast<uint4 *>(out) = make_uint4(q[0], q[1 % NC], q[2 % NC], q[3 % NC]); }
-            else { *reinterpret_cast<uint2 *>(out) = make_uint2(q[0], q[1 % NC]); }
-            out += out_w;
-        }
-    }
+    resize_strip_thread<S, T, NC>(src, in_w, in_h, out_w, y0, y1, strip, cx, cy, dst, int(blockIdx.x * 128 + threadIdx.x), int(blockIdx.y));
 }
 
 }// namespace vkt
